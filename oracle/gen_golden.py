@@ -1,0 +1,194 @@
+"""Pin the restated oracle against the UNMODIFIED reference and write tests/golden/*.npz.
+
+TEST INFRASTRUCTURE ONLY -- runs in the build container (needs /root/reference, which does not
+exist on the GPU box).  Usage:
+
+    python -m oracle.gen_golden omni      # OmniParser cases  -> tests/golden/omni_*.npz
+    python -m oracle.gen_golden mgp       # MGP-STR cases     -> tests/golden/mgp_*.npz
+    python -m oracle.gen_golden all       # both, each in its own interpreter (module-name clashes:
+                                          # both sub-projects define top-level `utils`, `models`)
+
+For every case the script (1) builds the reference nn.Module exactly as the reference drivers do
+(minus the CUDA hard-coding), (2) ``load_state_dict(strict=True)`` the
+synthetic checkpoint from oracle/weights.py, (3) runs the reference forward, (4) runs the
+restatement (oracle/omniparser_ref.py, oracle/mgpstr_ref.py) on the same inputs and asserts
+agreement, (5) stores the REFERENCE outputs as small fixtures.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(REPO, 'tests', 'golden')
+SHIM = os.path.join(REPO, 'oracle', 'shim')
+REF = '/root/reference/OCR'
+
+
+def _maxdiff(a, b):
+    return float((a.float() - b.float()).abs().max())
+
+
+def omni_inputs(case):
+    """Synthetic page + pad mask for a named case (shared with the tests)."""
+    g = torch.Generator().manual_seed(case['seed'])
+    H, Wd = case['canvas']
+    h, w = case.get('image', case['canvas'])
+    img = torch.zeros(1, 3, H, Wd)
+    img[:, :, :h, :w] = torch.randn(1, 3, h, w, generator=g)
+    mask = torch.ones(1, H, Wd, dtype=torch.bool)
+    mask[:, :h, :w] = False
+    return img, mask
+
+
+OMNI_CASES = {
+    # name: canvas (H,W), optional real image size, weights seed / eos bias, decode lengths
+    'full': dict(seed=1000, canvas=(96, 128), wseed=0, pt_eos_bias=-30.0, pt_seq_length=8, rec_length=25),
+    'masked': dict(seed=1001, canvas=(96, 128), image=(80, 112), wseed=0, pt_eos_bias=-30.0, pt_seq_length=6,
+                   rec_length=25),
+    'odd': dict(seed=1002, canvas=(108, 76), wseed=1, pt_eos_bias=-30.0, pt_seq_length=4, rec_length=25),
+    'eos': dict(seed=1003, canvas=(64, 64), wseed=0, pt_eos_bias=0.45, pt_seq_length=12, rec_length=25),
+    'oddlen': dict(seed=1005, canvas=(64, 64), wseed=0, pt_eos_bias=-30.0, pt_seq_length=5, rec_length=7),
+    'empty': dict(seed=1004, canvas=(64, 64), wseed=0, pt_eos_bias=30.0, pt_seq_length=8, rec_length=25),
+}
+
+
+def gen_omni():
+    sys.path[:0] = [SHIM, os.path.join(REF, 'OmniParser')]
+    tmp = tempfile.mktemp(suffix='.pth')
+    torch.save({'model': {}}, tmp)  # satisfies swin_transformer.py:636
+    from oracle import omniparser_ref as O
+    from oracle import weights as W
+    built = {}
+    for name, case in OMNI_CASES.items():
+        sys.argv = ['x', '--tfm_pre_norm', '--use_fpn', '--use_char_window_prompt', '--pretrained_file', tmp,
+                    '--pt_seq_length', str(case['pt_seq_length']), '--rec_length', str(case['rec_length'])]
+        from utils.parser import DefaultParser
+        from utils.nested_tensor import NestedTensor
+        from model.backbone import build_backbone
+        from model.transformer import build_transformer
+        from model.omniparser import OmniParser
+        args = DefaultParser().parse_args()
+        assert (args.pt_eos_index, args.rec_sos_index, args.padding_index, args.num_classes) == \
+               (W.PT_EOS, W.REC_SOS, W.PADDING, W.PADDING + 1)
+        key = (case['wseed'], case['pt_eos_bias'])
+        if key not in built:
+            built.clear()
+            built[key] = W.omniparser_state_dict(seed=case['wseed'], pt_eos_bias=case['pt_eos_bias'])
+        sd = built[key]
+        model = OmniParser(build_backbone(args), build_transformer(args), args.num_classes, True).eval()
+        missing = model.load_state_dict(sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        assert len(sd) == 610 and sum(v.numel() for k, v in sd.items() if 'relative_position_index' not in k) \
+            - 2 * 2 * 512 == sum(p.numel() for p in model.parameters()), 'key/param census (SURVEY 8b)'
+        img, mask = omni_inputs(case)
+        pt_prompt, poly_prompt, rec_prompt = O.default_prompts(True)
+        with torch.no_grad():
+            # ---- reference, staged --------------------------------------------------------------
+            feats, poss = model.backbone(NestedTensor(img, mask))
+            src = model.input_proj(model.fpn([x.tensors for x in feats]))
+            ref_mem = src.flatten(2).permute(0, 2, 1)[0]
+            ref_pos = poss[-2].flatten(2).permute(0, 2, 1)[0]
+            ref_kpm = feats[-2].mask.flatten(1)[0]
+            out = model(NestedTensor(img, mask), [pt_prompt, poly_prompt, rec_prompt,
+                                                  torch.tensor(case['canvas'])])
+            # ---- restatement --------------------------------------------------------------------
+            o_feats = O.swin_backbone(img, sd)
+            mem, pos, kpm, (h, w) = O.encode(img, mask, sd)
+            res, logs = O.greedy_text_spotting(mem[0], kpm[0], pos[0], sd, pt_prompt, case['pt_seq_length'],
+                                               case['rec_length'], return_logits=True)
+        for lvl in range(4):
+            d = _maxdiff(feats[lvl].tensors.permute(0, 2, 3, 1), o_feats[lvl])
+            assert d < 2e-5, (name, 'feature', lvl, d)
+        assert _maxdiff(ref_mem, mem[0]) < 2e-5 and _maxdiff(ref_pos, pos[0]) < 1e-6
+        assert torch.equal(ref_kpm, kpm[0])
+        gold = dict(memory=ref_mem.numpy(), pos=ref_pos.numpy(), kpm=ref_kpm.numpy(), hw=np.array([h, w]))
+        for lvl in range(4):  # strided samples of the four LN'd stage outputs (NHWC order)
+            gold[f'feat{lvl}_s'] = feats[lvl].tensors.permute(0, 2, 3, 1).reshape(-1)[::7].numpy()
+        if out is None:
+            assert res is None, name
+            gold['none'] = np.array([1])
+        else:
+            (pt, poly, rec), (probs,) = out
+            assert torch.equal(pt, res[0][0]) and torch.equal(poly, res[0][1]) and torch.equal(rec, res[0][2]), name
+            assert _maxdiff(probs, res[1][0]) < 1e-5
+            gold.update(none=np.array([0]), pt=pt.numpy(), poly=poly.numpy(), rec=rec.numpy(), probs=probs.numpy())
+            with torch.no_grad():  # teacher-forced logits from the reference's own decode()
+                n = pt.numel() // 2
+                tr = model.transformer
+                memory = src.flatten(2).permute(2, 0, 1)
+                posr = poss[-2].flatten(2).permute(2, 0, 1)
+                mk = feats[-2].mask.flatten(1)
+                pt_full = torch.cat([pt_prompt, pt], dim=1)
+                poly_full = torch.cat([pt.reshape(-1, 2), poly_prompt.repeat(n, 1), poly.reshape(n, 32)], dim=1)
+                rec_full = torch.cat([pt.reshape(-1, 2), rec_prompt.repeat(n, 1), rec[0]], dim=1)
+                tf = {'pt': tr.decode(pt_full, memory, mk, posr, 'pt'),
+                      'poly': tr.decode(poly_full, memory, mk, posr, 'poly'),
+                      'rec': tr.decode(rec_full, memory, mk, posr, 'rec')}
+                o_tf = {'pt': O.decode_logits(pt_full, mem[0], kpm[0], pos[0], sd, 'pt'),
+                        'poly': O.decode_logits(poly_full, mem[0], kpm[0], pos[0], sd, 'poly'),
+                        'rec': O.decode_logits(rec_full, mem[0], kpm[0], pos[0], sd, 'rec')}
+            for k in tf:
+                assert _maxdiff(tf[k], o_tf[k]) < 5e-5, (name, k, _maxdiff(tf[k], o_tf[k]))
+            gold['tf_pt'] = tf['pt'][0, 6:].numpy()            # logits that produced each pt token (+1)
+            gold['tf_poly'] = tf['poly'][:, [2, 17, 33]].numpy()
+            L = case['rec_length']
+            gold['tf_rec'] = tf['rec'][:, [2, 2 + L // 2, 2 + L - 1]].numpy()
+            texts, confs = O.decode_rec_strings(rec[0], probs)
+            gold['texts'] = np.array(texts)
+            gold['confs'] = np.array(confs, dtype=np.float64)
+        np.savez_compressed(os.path.join(GOLD, f'omni_{name}.npz'), **gold)
+        print(f'omni_{name}: ok  hw={h}x{w}  out={"None" if out is None else tuple(out[0][2].shape)}')
+
+
+MGP_CASES = {'b1': dict(seed=0, batch=1, wseed=0), 'b3': dict(seed=1, batch=3, wseed=0)}
+
+
+def gen_mgp():
+    sys.path[:0] = [SHIM, os.path.join(REF, 'MGP-STR')]
+    from oracle import mgpstr_ref as M
+    from oracle import weights as W
+    from modules.mgp_str import create_mgp_str  # noqa: the reference factory (mgp_str.py:33-44)
+    model = create_mgp_str(batch_max_length=27, num_tokens=38, model='mgp_str_base_patch4_3_32_128').eval()
+    sd = W.mgpstr_state_dict(seed=0)
+    bare = {k[len('module.mgp_str.'):]: v for k, v in sd.items()}
+    r = model.load_state_dict(bare, strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    for name, case in MGP_CASES.items():
+        g = torch.Generator().manual_seed(case['seed'])
+        img = torch.rand(case['batch'], 3, 32, 128, generator=g)
+        with torch.no_grad():
+            attens, char, bpe, wp = model(img, is_eval=True)
+            o = M.forward(img, sd)
+        for a, b in zip(attens, o[0]):
+            assert _maxdiff(a, b) < 1e-6
+        for a, b in zip((char, bpe, wp), o[1:]):
+            assert _maxdiff(a, b) < 2e-5, _maxdiff(a, b)
+        gold = dict(char=char.numpy(), char_attn=attens[0].numpy())
+        for nm, lg in (('bpe', bpe), ('wp', wp)):
+            gold[nm + '_ids'] = lg.argmax(-1).numpy()
+            gold[nm + '_max'] = lg.max(-1)[0].numpy()
+            gold[nm + '_prob'] = lg.softmax(-1).max(-1)[0].numpy()
+            gold[nm + '_s'] = lg.reshape(-1)[::997].numpy()
+        gold['bpe_attn_s'] = attens[1].reshape(-1)[::5].numpy()
+        gold['wp_attn_s'] = attens[2].reshape(-1)[::5].numpy()
+        np.savez_compressed(os.path.join(GOLD, f'mgp_{name}.npz'), **gold)
+        print(f'mgp_{name}: ok')
+
+
+if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_grad_enabled(False)
+    if which == 'all':
+        for w in ('omni', 'mgp'):
+            subprocess.check_call([sys.executable, '-m', 'oracle.gen_golden', w], cwd=REPO)
+    elif which == 'omni':
+        gen_omni()
+    else:
+        gen_mgp()

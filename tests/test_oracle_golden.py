@@ -1,0 +1,66 @@
+"""CPU: the restated oracle reproduces the fixtures written from the UNMODIFIED reference
+(oracle/gen_golden.py).  This is what pins the oracle on a box without /root/reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mgpstr_ref as M
+from oracle import omniparser_ref as O
+from oracle.gen_golden import MGP_CASES, OMNI_CASES, omni_inputs
+from tests.conftest import mgp_sd, omni_sd
+
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize('name', ['full', 'masked', 'odd', 'eos', 'oddlen', 'empty'])
+def test_omniparser_oracle_matches_reference_fixture(name, golden_dir):
+    case = OMNI_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f'omni_{name}.npz'))
+    sd = omni_sd(case['wseed'], case['pt_eos_bias'])
+    img, mask = omni_inputs(case)
+    feats = O.swin_backbone(img, sd)
+    for lvl in range(4):
+        np.testing.assert_allclose(feats[lvl].reshape(-1)[::7].numpy(), gold[f'feat{lvl}_s'], atol=3e-5, rtol=0)
+    mem, pos, kpm, (h, w) = O.encode(img, mask, sd)
+    assert (h, w) == tuple(gold['hw'])
+    np.testing.assert_allclose(mem[0].numpy(), gold['memory'], atol=3e-5, rtol=0)
+    np.testing.assert_allclose(pos[0].numpy(), gold['pos'], atol=2e-6, rtol=0)
+    assert np.array_equal(kpm[0].numpy(), gold['kpm'])
+    pt_prompt, _, _ = O.default_prompts(True)
+    res = O.greedy_text_spotting(mem[0], kpm[0], pos[0], sd, pt_prompt, case['pt_seq_length'], case['rec_length'])
+    if gold['none'][0]:
+        assert res is None
+        return
+    (pt, poly, rec), (probs,) = res
+    assert np.array_equal(pt.numpy(), gold['pt'])
+    assert np.array_equal(poly.numpy(), gold['poly'])
+    assert np.array_equal(rec.numpy(), gold['rec'])
+    np.testing.assert_allclose(probs.numpy(), gold['probs'], atol=1e-5, rtol=0)
+    texts, confs = O.decode_rec_strings(rec[0], probs)
+    assert texts == gold['texts'].tolist()
+    np.testing.assert_allclose(np.array(confs), gold['confs'], rtol=1e-4)
+
+
+@pytest.mark.parametrize('name', ['b1', 'b3'])
+def test_mgpstr_oracle_matches_reference_fixture(name, golden_dir):
+    case = MGP_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f'mgp_{name}.npz'))
+    g = torch.Generator().manual_seed(case['seed'])
+    img = torch.rand(case['batch'], 3, 32, 128, generator=g)
+    attns, char, bpe, wp = M.forward(img, mgp_sd(case['wseed']))
+    np.testing.assert_allclose(char.numpy(), gold['char'], atol=3e-5, rtol=0)
+    np.testing.assert_allclose(attns[0].numpy(), gold['char_attn'], atol=1e-6, rtol=0)
+    for nm, lg in (('bpe', bpe), ('wp', wp)):
+        assert np.array_equal(lg.argmax(-1).numpy(), gold[nm + '_ids'])
+        np.testing.assert_allclose(lg.max(-1)[0].numpy(), gold[nm + '_max'], atol=3e-5, rtol=0)
+        np.testing.assert_allclose(lg.reshape(-1)[::997].numpy(), gold[nm + '_s'], atol=3e-5, rtol=0)
+
+
+def test_vocab_layout():
+    """Token-id layout of OCR/OmniParser/utils/parser.py:91-103."""
+    from oracle import weights as W
+    assert (W.RECOG_PAD, W.PT_EOS, W.POLY_EOS, W.REC_EOS, W.PT_SOS, W.POLY_SOS, W.REC_SOS, W.PADDING) == \
+           (1096, 1097, 1098, 1099, 1100, 1101, 1102, 1103)
+    assert len(W.CHARS) == 95
