@@ -1,0 +1,143 @@
+"""ctypes binding of libalm_ocr.so (include/alm_ocr.h).
+
+There is no fallback: if the shared library is missing or cannot be loaded this module raises, and
+every adapter built on it fails loudly.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make`` at the repo root.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libalm_ocr.so')
+
+ALM_OK = 0
+MODEL_OMNI_SPOT, MODEL_OMNI_KIE, MODEL_MGPSTR = 1, 2, 3
+DT_F32, DT_F16, DT_BF16, DT_I64 = 0, 1, 2, 3
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [('name', C.c_char_p), ('data', C.c_void_p), ('dtype', C.c_int), ('ndim', C.c_int),
+                ('shape', C.c_int64 * 4)]
+
+
+class DecodeCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        'num_bins', 'pt_eos', 'poly_eos', 'rec_eos', 'pt_sos', 'poly_sos', 'rec_sos', 'recog_pad',
+        'pt_seq_length', 'rec_length', 'poly_length', 'vie_categories', 'max_instances')]
+
+
+class AlmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'libalm_ocr error {code}: {msg}')
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/alm_ocr.h
+SIGNATURES = {
+    'alm_init': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    'alm_free': (None, [C.c_void_p]),
+    'alm_last_error': (C.c_char_p, [C.c_void_p]),
+    'alm_version': (C.c_char_p, []),
+    'alm_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
+    'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
+    'alm_load_weights': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorDesc), C.c_int]),
+    'alm_omni_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    'alm_omni_get_feature': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'alm_omni_get_memory': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    'alm_omni_memory_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'alm_omni_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    'alm_omni_decode_logits': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'alm_omni_vocab': (C.c_int, [C.c_void_p]),
+    'alm_mgpstr_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    'alm_op_linear': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int]),
+    'alm_op_layernorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_long,
+                                   C.c_int]),
+    'alm_op_window_attention': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int]),
+}
+
+
+def load():
+    """dlopen libalm_ocr.so and bind every symbol of include/alm_ocr.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} not found: build it first (make / __graft_entry__.build()); '
+                          'there is no CPU or PyTorch fallback')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One alm_ctx: one GPU, one stream, not thread-safe."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.alm_init(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != ALM_OK:
+            raise AlmError(rc, 'alm_init failed (no sm_100a CUDA device? this library has no fallback path)')
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != ALM_OK:
+            raise AlmError(rc, self.lib.alm_last_error(self.h).decode())
+
+    def set_option(self, key: str, value: int):
+        self.check(self.lib.alm_set_option(self.h, key.encode(), int(value)))
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.alm_launch_count(self.h, 1 if reset else 0))
+
+    def load_state_dict(self, kind: int, state_dict):
+        """state_dict: name -> torch.Tensor (any device) in the reference checkpoint layout."""
+        import torch
+        descs = (TensorDesc * len(state_dict))()
+        keep = []
+        for i, (k, v) in enumerate(state_dict.items()):
+            t = v.detach().to('cpu').contiguous()
+            if t.dtype == torch.float32:
+                dt = DT_F32
+            elif t.dtype == torch.float16:
+                dt = DT_F16
+            elif t.dtype == torch.bfloat16:
+                dt = DT_BF16
+            elif t.dtype == torch.int64:
+                dt = DT_I64
+            else:
+                t = t.float()
+                dt = DT_F32
+            keep.append(t)
+            assert t.dim() <= 4, k
+            descs[i].name = k.encode()
+            descs[i].data = t.data_ptr()
+            descs[i].dtype = dt
+            descs[i].ndim = t.dim()
+            for j, s in enumerate(t.shape):
+                descs[i].shape[j] = s
+        self.check(self.lib.alm_load_weights(self.h, kind, descs, len(state_dict)))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.alm_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,175 @@
+// Internal declarations shared by the CUDA translation units of libalm_ocr.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/alm_ocr.h"
+
+namespace alm {
+
+typedef __nv_bfloat16 bf16;
+
+struct AlmError {
+  int code;
+  std::string msg;
+};
+
+#define ALM_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw alm::AlmError{ALM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                            ":" + std::to_string(__LINE__) + ")"};                \
+  } while (0)
+
+#define ALM_REQUIRE(cond, code, message)                          \
+  do {                                                            \
+    if (!(cond)) throw alm::AlmError{(code), std::string(message) + " [" #cond "]"}; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// bump allocator over one cudaMalloc'ed slab (activations); weights use their own slab
+// ---------------------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 1023) & ~size_t(1023);
+    if (a + bytes > cap)
+      throw AlmError{ALM_ERR_OOM, "workspace arena exhausted: need " + std::to_string(a + bytes) + " of " +
+                                      std::to_string(cap) + " bytes (raise alm_set_option workspace_mb)"};
+    off = a + bytes;
+    if (off > high) high = off;
+    return base + a;
+  }
+  template <class T>
+  T* get(size_t n) {
+    return reinterpret_cast<T*>(alloc(n * sizeof(T)));
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+// K-major bf16 operand (hi/lo split pair), optionally batched over two batch dims.
+struct Operand {
+  const bf16* hi = nullptr;
+  const bf16* lo = nullptr;  // may be null when the context runs single-pass bf16
+  int rows = 0;              // per batch
+  int K = 0;
+  long ld = 0;               // row stride, elements (multiple of 8)
+  int nb0 = 1, nb1 = 1;      // batch extents (1 + stride 0 == broadcast)
+  long bs0 = 0, bs1 = 0;     // batch strides, elements (multiples of 8)
+};
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+enum { BIAS_NONE = 0, BIAS_COL = 1, BIAS_ROW = 2 };
+
+// out[orow, n] = act(alpha * acc + bias) + resid[rrow, n]
+//   orow = out_map ? out_map[row] : row   (negative -> row is dropped)
+//   rrow = resid_map ? resid_map[row] : orow
+// Output is fp32 (out_f32) and/or a split bf16 pair (out_hi / out_lo) usable as the next GEMM's operand.
+struct Epilogue {
+  float* out_f32 = nullptr;
+  bf16* out_hi = nullptr;
+  bf16* out_lo = nullptr;
+  long ldo = 0, obs0 = 0, obs1 = 0;  // fp32 and bf16 outputs share geometry
+  const float* bias = nullptr;
+  int bias_mode = BIAS_NONE;
+  long bias_bs0 = 0;  // per-batch(b0) bias stride
+  const float* resid = nullptr;
+  long ldr = 0, rbs0 = 0, rbs1 = 0;
+  const int* out_map = nullptr;
+  const int* resid_map = nullptr;
+  int act = ACT_NONE;
+  float alpha = 1.0f;
+};
+
+struct Ctx;
+
+void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E);
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+struct HostTensor {
+  std::vector<float> f32;  // converted to fp32 on load
+  std::vector<int64_t> shape;
+  size_t numel() const { return f32.size(); }
+};
+
+struct SplitW {  // [N, Kpad] row-major bf16 hi/lo, K padded to a multiple of 8 with zeros
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int N = 0, K = 0, ld = 0;
+  Operand op() const {
+    Operand o;
+    o.hi = hi; o.lo = lo; o.rows = N; o.K = K; o.ld = ld;
+    return o;
+  }
+};
+
+struct OmniModel;
+struct MgpModel;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  std::string err;
+  Arena ws;
+  size_t ws_bytes = size_t(24) << 30;
+  int gemm_impl = 0;  // 0 = tcgen05, 1 = SIMT debug kernel
+  int nsplit = 3;     // 3 = bf16x3 split (fp32-class), 1 = single-pass bf16
+  PFN_encodeTiled encode = nullptr;
+  long launches = 0;  // kernels launched since last reset (gpu_launches in bench.py)
+  OmniModel* omni = nullptr;
+  MgpModel* mgp = nullptr;
+  std::vector<void*> weight_slabs;
+  // weight slab bump allocator
+  char* wbase = nullptr;
+  size_t wcap = 0, woff = 0;
+  void* walloc(size_t bytes);
+  void ensure_ws();
+};
+
+// weight helpers (weights.cu)
+const HostTensor& need(const std::map<std::string, HostTensor>& m, const std::string& k);
+float* upload_f32(Ctx* c, const float* h, size_t n);
+SplitW upload_split(Ctx* c, const float* w, int N, int K, int Kpad);  // w is [N,K] row-major fp32; Kpad<=0 -> round up to 8
+int* upload_i32(Ctx* c, const std::vector<int>& v);
+
+// ---------------------------------------------------------------------------------------------
+// elementwise / gather / attention kernels (kernels.cu)
+// ---------------------------------------------------------------------------------------------
+// Gather `nsrc` source rows of width Cs (fp32, row stride lds) into one row of width C = nsrc*Cs, optional
+// LayerNorm over C, write fp32 and/or split bf16.  map[r*nsrc + s] = source row or -1 (zeros).
+// zero_missing: a row whose (single) source is -1 is written as zeros *without* LN/affine ("pad after norm").
+void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int Cs, long rows, const float* gamma,
+               const float* beta, float eps, bool zero_missing, const float* add, long ld_add, float* out_f32,
+               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo);
+
+void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp, bf16* hi, bf16* lo);
+
+void window_attention(Ctx* c, const float* qkv, int C, int heads, int nWh, int nWw, int B, int shift, int Hp, int Wp,
+                      const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
+
+void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo);
+
+void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint8_t* kpm, int rows_per_mask,
+                  long mask_ld, float* out_f32, bf16* out_hi, bf16* out_lo, long ldo);
+
+void count_launch(Ctx* c, int n = 1);
+void check_launch(const char* what);
+
+}  // namespace alm

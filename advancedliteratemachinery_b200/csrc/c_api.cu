@@ -1,0 +1,351 @@
+// extern "C" surface of libalm_ocr.so (include/alm_ocr.h).  Nothing throws across this boundary.
+#include <string.h>
+
+#include <algorithm>
+
+#include "alm_internal.h"
+#include "mgp.h"
+#include "omni.h"
+
+using namespace alm;
+
+struct alm_ctx {
+  Ctx c;
+  void* dev_in = nullptr;  // staging for host-resident inputs
+  size_t dev_in_bytes = 0;
+  void* dev_mask = nullptr;
+  size_t dev_mask_bytes = 0;
+};
+
+namespace {
+
+template <class F>
+int guarded(alm_ctx* h, F&& f) {
+  if (!h) return ALM_ERR_INVALID;
+  try {
+    cudaSetDevice(h->c.device);
+    f();
+    h->c.err.clear();
+    return ALM_OK;
+  } catch (const AlmError& e) {
+    h->c.err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->c.err = std::string("exception: ") + e.what();
+    return ALM_ERR_INVALID;
+  } catch (...) {
+    h->c.err = "unknown exception";
+    return ALM_ERR_INVALID;
+  }
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// returns a device pointer for `p` (host buffers are copied into the context's staging slab on the stream)
+const void* stage_input(alm_ctx* h, const void* p, size_t bytes, void** slab, size_t* slab_bytes) {
+  if (p == nullptr) return nullptr;
+  if (is_device_ptr(p)) return p;
+  if (*slab_bytes < bytes) {
+    if (*slab) cudaFree(*slab);
+    *slab = nullptr;
+    *slab_bytes = 0;
+    if (cudaMalloc(slab, bytes) != cudaSuccess) throw AlmError{ALM_ERR_OOM, "cudaMalloc of the input staging buffer failed"};
+    *slab_bytes = bytes;
+  }
+  ALM_CHECK_CUDA(cudaMemcpyAsync(*slab, p, bytes, cudaMemcpyHostToDevice, h->c.stream));
+  return *slab;
+}
+
+void d2h(Ctx* c, void* dst, const void* src, size_t bytes) {
+  ALM_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+
+float bf16_bits_to_f32(uint16_t v) {
+  uint32_t u = static_cast<uint32_t>(v) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+float f16_bits_to_f32(uint16_t v) {
+  const uint32_t s = (v >> 15) & 1, e = (v >> 10) & 31, m = v & 1023;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) u = s << 31;
+    else {
+      int ee = -1;
+      uint32_t mm = m;
+      do { ++ee; mm <<= 1; } while ((mm & 1024) == 0);
+      u = (s << 31) | ((127 - 15 - ee) << 23) | ((mm & 1023) << 13);
+    }
+  } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
+  else u = (s << 31) | ((e - 15 + 127) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* alm_version(void) { return "alm_ocr 0.1 (sm_100a, tcgen05)"; }
+
+int alm_init(int device, void* stream, alm_ctx** out) {
+  if (!out) return ALM_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    cudaGetLastError();
+    return ALM_ERR_CUDA;  // no CUDA device: the library has no CPU fallback
+  }
+  alm_ctx* h = new alm_ctx();
+  h->c.device = device;
+  int rc = guarded(h, [&] {
+    ALM_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ALM_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    ALM_REQUIRE(prop.major == 10, ALM_ERR_UNSUPPORTED,
+                "libalm_ocr is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    h->c.num_sms = prop.multiProcessorCount;
+    if (stream) h->c.stream = static_cast<cudaStream_t>(stream);
+    else {
+      ALM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+      h->c.own_stream = true;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ALM_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    ALM_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, ALM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    h->c.encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  });
+  if (rc != ALM_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return ALM_OK;
+}
+
+void alm_free(alm_ctx* h) {
+  if (!h) return;
+  cudaSetDevice(h->c.device);
+  cudaStreamSynchronize(h->c.stream);
+  delete h->c.omni;
+  mgp_free(h->c.mgp);
+  for (void* p : h->c.weight_slabs) cudaFree(p);
+  if (h->c.ws.base) cudaFree(h->c.ws.base);
+  if (h->dev_in) cudaFree(h->dev_in);
+  if (h->dev_mask) cudaFree(h->dev_mask);
+  if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
+  delete h;
+}
+
+const char* alm_last_error(const alm_ctx* h) { return h ? h->c.err.c_str() : "null context"; }
+
+int alm_set_option(alm_ctx* h, const char* key, long value) {
+  return guarded(h, [&] {
+    const std::string k = key ? key : "";
+    if (k == "nsplit") {
+      ALM_REQUIRE(value == 1 || value == 3, ALM_ERR_INVALID, "nsplit must be 1 or 3");
+      h->c.nsplit = static_cast<int>(value);
+    } else if (k == "gemm_impl") {
+      ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "gemm_impl must be 0 or 1");
+      h->c.gemm_impl = static_cast<int>(value);
+    } else if (k == "workspace_mb") {
+      ALM_REQUIRE(value >= 64 && h->c.ws.base == nullptr, ALM_ERR_STATE, "workspace_mb must be set before first use");
+      h->c.ws_bytes = static_cast<size_t>(value) << 20;
+    } else {
+      throw AlmError{ALM_ERR_INVALID, "unknown option " + k};
+    }
+  });
+}
+
+long alm_launch_count(alm_ctx* h, int reset) {
+  if (!h) return -1;
+  const long n = h->c.launches;
+  if (reset) h->c.launches = 0;
+  return n;
+}
+
+int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors, int n) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(tensors && n > 0, ALM_ERR_INVALID, "empty state dict");
+    std::map<std::string, HostTensor> t;
+    for (int i = 0; i < n; ++i) {
+      const alm_tensor_desc& d = tensors[i];
+      ALM_REQUIRE(d.name && d.data && d.ndim >= 0 && d.ndim <= 4, ALM_ERR_INVALID, "bad tensor descriptor");
+      HostTensor ht;
+      size_t numel = 1;
+      for (int k = 0; k < d.ndim; ++k) {
+        ht.shape.push_back(d.shape[k]);
+        numel *= static_cast<size_t>(d.shape[k]);
+      }
+      ht.f32.resize(numel);
+      switch (d.dtype) {
+        case ALM_F32: memcpy(ht.f32.data(), d.data, numel * 4); break;
+        case ALM_F16:
+          for (size_t j = 0; j < numel; ++j) ht.f32[j] = f16_bits_to_f32(static_cast<const uint16_t*>(d.data)[j]);
+          break;
+        case ALM_BF16:
+          for (size_t j = 0; j < numel; ++j) ht.f32[j] = bf16_bits_to_f32(static_cast<const uint16_t*>(d.data)[j]);
+          break;
+        case ALM_I64:
+          for (size_t j = 0; j < numel; ++j) ht.f32[j] = static_cast<float>(static_cast<const int64_t*>(d.data)[j]);
+          break;
+        default: throw AlmError{ALM_ERR_INVALID, std::string("unknown dtype for ") + d.name};
+      }
+      t.emplace(d.name, std::move(ht));
+    }
+    if (model_kind == ALM_MODEL_OMNI_SPOT || model_kind == ALM_MODEL_OMNI_KIE) omni_load(&h->c, model_kind, t);
+    else if (model_kind == ALM_MODEL_MGPSTR) mgp_load(&h->c, t);
+    else throw AlmError{ALM_ERR_INVALID, "unknown model kind"};
+    ALM_CHECK_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+// ------------------------------------------------------------------------------------------ OmniParser
+int alm_omni_encode(alm_ctx* h, const float* img, const uint8_t* mask, int B, int H, int W) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(img != nullptr && B > 0 && H > 0 && W > 0, ALM_ERR_INVALID, "alm_omni_encode arguments");
+    const size_t px = static_cast<size_t>(B) * H * W;
+    const float* dimg = static_cast<const float*>(stage_input(h, img, px * 3 * sizeof(float), &h->dev_in, &h->dev_in_bytes));
+    const uint8_t* dmask = static_cast<const uint8_t*>(stage_input(h, mask, px, &h->dev_mask, &h->dev_mask_bytes));
+    omni_encode(&h->c, dimg, dmask, B, H, W);
+  });
+}
+
+int alm_omni_memory_shape(alm_ctx* h, int* B, int* mh, int* mw) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(h->c.omni && h->c.omni->encoded, ALM_ERR_STATE, "no encoded batch");
+    if (B) *B = h->c.omni->B;
+    if (mh) *mh = h->c.omni->mh;
+    if (mw) *mw = h->c.omni->mw;
+  });
+}
+
+int alm_omni_vocab(alm_ctx* h) { return (h && h->c.omni) ? h->c.omni->V : ALM_ERR_STATE; }
+
+int alm_omni_get_feature(alm_ctx* h, int level, float* out, size_t out_elems) {
+  return guarded(h, [&] {
+    OmniModel* m = h->c.omni;
+    ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "no encoded batch");
+    ALM_REQUIRE(level >= 0 && level < 4 && out, ALM_ERR_INVALID, "feature level");
+    const size_t n = static_cast<size_t>(m->B) * m->Hs[level] * m->Ws[level] * (128 << level);
+    ALM_REQUIRE(out_elems == n, ALM_ERR_INVALID, "feature buffer size mismatch: expected " + std::to_string(n));
+    d2h(&h->c, out, m->feat[level], n * sizeof(float));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+  });
+}
+
+int alm_omni_get_memory(alm_ctx* h, int which, float* out, size_t out_elems) {
+  return guarded(h, [&] {
+    OmniModel* m = h->c.omni;
+    ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "no encoded batch");
+    const size_t n = static_cast<size_t>(m->B) * m->M * 512;
+    ALM_REQUIRE(out && out_elems == n && (which == 0 || which == 1), ALM_ERR_INVALID, "memory buffer size mismatch");
+    d2h(&h->c, out, which == 0 ? m->memory : m->pos, n * sizeof(float));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+  });
+}
+
+int alm_omni_decode(alm_ctx* h, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_inst,
+                    int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(pt_prompt && cfg && n_inst && pt && poly && rec && rec_prob, ALM_ERR_INVALID, "null argument");
+    omni_decode(&h->c, pt_prompt, n_prompt, *cfg, n_inst, pt, poly, rec, rec_prob);
+  });
+}
+
+int alm_omni_decode_logits(alm_ctx* h, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(seq && logits, ALM_ERR_INVALID, "null argument");
+    omni_decode_logits(&h->c, image, kind, seq, n_seq, len, logits);
+  });
+}
+
+// ------------------------------------------------------------------------------------------ MGP-STR
+int alm_mgpstr_forward(alm_ctx* h, const float* img, int B, float* attn, float* char_logits, float* bpe_logits,
+                       float* wp_logits, int32_t* ids, float* prob) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(img && B > 0, ALM_ERR_INVALID, "alm_mgpstr_forward arguments");
+    const float* dimg = static_cast<const float*>(
+        stage_input(h, img, static_cast<size_t>(B) * 3 * 32 * 128 * sizeof(float), &h->dev_in, &h->dev_in_bytes));
+    mgp_forward(&h->c, dimg, B, attn, char_logits, bpe_logits, wp_logits, ids, prob);
+  });
+}
+
+// ------------------------------------------------------------------------------------------ unit ops
+int alm_op_linear(alm_ctx* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
+                  int batch) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0 && batch > 0, ALM_ERR_INVALID, "alm_op_linear arguments");
+    ALM_REQUIRE(is_device_ptr(A) && is_device_ptr(W) && is_device_ptr(C), ALM_ERR_INVALID, "device pointers required");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    const int Kp = (K + 7) & ~7;
+    bf16* ah = c->ws.get<bf16>(static_cast<size_t>(batch) * M * Kp);
+    bf16* al = c->ws.get<bf16>(static_cast<size_t>(batch) * M * Kp);
+    bf16* wh = c->ws.get<bf16>(static_cast<size_t>(batch) * N * Kp);
+    bf16* wl = c->ws.get<bf16>(static_cast<size_t>(batch) * N * Kp);
+    if (Kp != K) {
+      ALM_CHECK_CUDA(cudaMemsetAsync(ah, 0, static_cast<size_t>(batch) * M * Kp * 2, c->stream));
+      ALM_CHECK_CUDA(cudaMemsetAsync(al, 0, static_cast<size_t>(batch) * M * Kp * 2, c->stream));
+      ALM_CHECK_CUDA(cudaMemsetAsync(wh, 0, static_cast<size_t>(batch) * N * Kp * 2, c->stream));
+      ALM_CHECK_CUDA(cudaMemsetAsync(wl, 0, static_cast<size_t>(batch) * N * Kp * 2, c->stream));
+    }
+    ALM_REQUIRE(K % 4 == 0, ALM_ERR_UNSUPPORTED, "alm_op_linear: K must be a multiple of 4");
+    split_rows(c, A, K, static_cast<long>(batch) * M, K, ah, al, Kp);
+    split_rows(c, W, K, static_cast<long>(batch) * N, K, wh, wl, Kp);
+    Operand a, b;
+    a.hi = ah; a.lo = al; a.rows = M; a.K = K; a.ld = Kp; a.nb0 = batch; a.bs0 = static_cast<long>(M) * Kp;
+    b.hi = wh; b.lo = wl; b.rows = N; b.K = K; b.ld = Kp; b.nb0 = batch; b.bs0 = static_cast<long>(N) * Kp;
+    Epilogue e;
+    e.out_f32 = C; e.ldo = N; e.obs0 = static_cast<long>(M) * N;
+    e.bias = bias; e.bias_mode = bias ? BIAS_COL : BIAS_NONE; e.act = act;
+    gemm(c, a, b, e);
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    c->ws.release(mk);
+  });
+}
+
+int alm_op_layernorm(alm_ctx* h, const float* x, const float* gamma, const float* beta, float eps, float* y, long rows,
+                     int C) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(x && gamma && beta && y && rows > 0, ALM_ERR_INVALID, "alm_op_layernorm arguments");
+    gather_ln(&h->c, x, C, nullptr, 1, C, rows, gamma, beta, eps, false, nullptr, 0, y, C, nullptr, nullptr, 0, nullptr,
+              nullptr);
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+  });
+}
+
+int alm_op_window_attention(alm_ctx* h, const float* qkv, const float* bias_table, float* out, int B, int nWh, int nWw,
+                            int C, int heads, int shift) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(qkv && bias_table && out, ALM_ERR_INVALID, "alm_op_window_attention arguments");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    std::vector<float> tab(static_cast<size_t>(169) * heads), dense(static_cast<size_t>(heads) * 2401);
+    ALM_CHECK_CUDA(cudaMemcpy(tab.data(), bias_table, tab.size() * 4, cudaMemcpyDeviceToHost));
+    for (int hh = 0; hh < heads; ++hh)
+      for (int i = 0; i < 49; ++i)
+        for (int j = 0; j < 49; ++j)
+          dense[static_cast<size_t>(hh) * 2401 + i * 49 + j] =
+              tab[static_cast<size_t>((i / 7 - j / 7 + 6) * 13 + (i % 7 - j % 7 + 6)) * heads + hh];
+    float* dd = c->ws.get<float>(dense.size());
+    ALM_CHECK_CUDA(cudaMemcpyAsync(dd, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    window_attention(c, qkv, C, heads, nWh, nWw, B, shift, nWh * 7, nWw * 7, dd, nullptr, nullptr, out);
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    c->ws.release(mk);
+  });
+}
+
+}  // extern "C"

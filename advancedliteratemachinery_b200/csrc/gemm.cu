@@ -1,0 +1,440 @@
+// The GEMM engine of the OCR forward path: D = A * B^T for K-major bf16 operands on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA into 128B-swizzled shared memory,
+// persistent warp-specialised CTAs (one per SM):
+//
+//     warp 0          : TMA producer       (one elected lane)
+//     warp 1          : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//     warps 2..5      : epilogue           (TMEM -> registers -> fused bias/act/residual/scatter -> global)
+//
+// Precision: the reference computes in fp32.  bf16 tensor-core operands alone would miss the
+// "logits within 1e-3" bar, so every fp32 matrix is carried as a (hi, lo) bf16 pair with hi + lo == x to
+// ~2^-17 and each K-step issues three MMAs (hi*hi + lo*hi + hi*lo) into the same fp32 TMEM accumulator
+// (NSPLIT = 3).  NSPLIT = 1 is the plain single-pass bf16 mode.
+//
+// Every linear layer of Swin-B / the decoder / ViT, the FPN 1x1 convolutions, the decoder cross-attention
+// (Q K^T and P V as batched GEMMs) and the vocabulary heads go through this one kernel.
+#include <algorithm>
+
+#include "alm_internal.h"
+#include "ptx.cuh"
+
+namespace alm {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+struct GemmParams {
+  int M, N, K;
+  int nb0, nb1;          // batch extents of the problem
+  int a_b0, a_b1;        // 1 if operand A varies along that batch dim (else coordinate 0 = broadcast)
+  int b_b0, b_b1;
+  int m_blocks, n_blocks, k_blocks;
+  long num_tiles;
+  Epilogue e;
+  int vec_ok;  // rows are 16-byte addressable -> vector stores
+};
+
+template <int BLOCK_N, int NSPLIT>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kNumA = (NSPLIT == 3) ? 2 : 1;
+  static constexpr int kNumB = (NSPLIT == 3) ? 2 : 1;
+  static constexpr int kStageBytes = kNumA * kABytes + kNumB * kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BLOCK_N, int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const GemmParams p) {
+  using L = SmemLayout<BLOCK_N, NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + L::kStages;
+  uint64_t* tmem_full = empty_bar + L::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_b_hi);
+    if (NSPLIT == 3) {
+      ptx::prefetch_tmap(&tm_a_lo);
+      ptx::prefetch_tmap(&tm_b_lo);
+    }
+    for (int s = 0; s < L::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long tiles_per_batch = static_cast<long>(p.m_blocks) * p.n_blocks;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int batch = static_cast<int>(tile / tiles_per_batch);
+        const int rem = static_cast<int>(tile % tiles_per_batch);
+        const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
+        const int b0 = batch % p.nb0, b1 = batch / p.nb0;
+        const int a0 = p.a_b0 ? b0 : 0, a1 = p.a_b1 ? b1 : 0;
+        const int w0 = p.b_b0 ? b0 : 0, w1 = p.b_b1 ? b1 : 0;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = stage_base + stage * L::kStageBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
+          if (NSPLIT == 3)
+            ptx::tma_load_4d(st + L::kABytes, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
+          uint8_t* sb = st + L::kNumA * L::kABytes;
+          ptx::tma_load_4d(sb, &tm_b_hi, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
+          if (NSPLIT == 3)
+            ptx::tma_load_4d(sb + L::kBBytes, &tm_b_lo, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
+          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
+                                 (uint32_t(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(stage_base + stage * L::kStageBytes);
+          const uint32_t a_lo = a_hi + L::kABytes;
+          const uint32_t b_hi = a_hi + L::kNumA * L::kABytes;
+          const uint32_t b_lo = b_hi + L::kBBytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128 B swizzle row
+            const uint64_t da = ptx::make_kmajor_sw128_desc(a_hi + koff);
+            const uint64_t db = ptx::make_kmajor_sw128_desc(b_hi + koff);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (NSPLIT == 3) {
+              const uint64_t dal = ptx::make_kmajor_sw128_desc(a_lo + koff);
+              const uint64_t dbl = ptx::make_kmajor_sw128_desc(b_lo + koff);
+              ptx::umma_bf16(d_tmem, dal, db, idesc, 1);
+              ptx::umma_bf16(d_tmem, da, dbl, idesc, 1);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const Epilogue& e = p.e;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int batch = static_cast<int>(tile / tiles_per_batch);
+      const int rem = static_cast<int>(tile % tiles_per_batch);
+      const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
+      const int b0 = batch % p.nb0, b1 = batch / p.nb0;
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      long orow = row;
+      if (row_ok && e.out_map) orow = e.out_map[row];
+      const bool store_ok = row_ok && orow >= 0;
+      long rrow = orow;
+      if (store_ok && e.resid_map) rrow = e.resid_map[row];
+      const long obase = static_cast<long>(b0) * e.obs0 + static_cast<long>(b1) * e.obs1 + orow * e.ldo;
+      const float* rptr =
+          e.resid ? e.resid + static_cast<long>(b0) * e.rbs0 + static_cast<long>(b1) * e.rbs1 + rrow * e.ldr : nullptr;
+      const float* bias = e.bias ? e.bias + static_cast<long>(b0) * e.bias_bs0 : nullptr;
+      const float row_bias = (bias && e.bias_mode == BIAS_ROW && row_ok) ? bias[row] : 0.0f;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + c * 32, v);
+        ptx::tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (!store_ok || col0 >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * e.alpha + row_bias;
+        const bool full = (col0 + 32 <= p.N) && p.vec_ok;
+        if (full) {
+          if (bias && e.bias_mode == BIAS_COL) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + col0 + j);
+              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+            }
+          }
+          if (e.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          } else if (e.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (rptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(rptr + col0 + j);
+              f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
+            }
+          }
+          if (e.out_f32) {
+            float4* o = reinterpret_cast<float4*>(e.out_f32 + obase + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (e.out_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              bf16 h0, l0, h1, l1;
+              split_bf16(f[2 * j], h0, l0);
+              split_bf16(f[2 * j + 1], h1, l1);
+              hi[j] = pack_bf16(h0, h1);
+              lo[j] = pack_bf16(l0, l1);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(e.out_hi + obase + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (e.out_lo) {
+              uint4* ol = reinterpret_cast<uint4*>(e.out_lo + obase + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        } else {
+          // ragged / unaligned tail: scalar, guarded
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col >= p.N) break;
+            float x = f[j];
+            if (bias && e.bias_mode == BIAS_COL) x += bias[col];
+            if (e.act == ACT_GELU) x = gelu_erf(x);
+            else if (e.act == ACT_RELU) x = fmaxf(x, 0.0f);
+            if (rptr) x += rptr[col];
+            if (e.out_f32) e.out_f32[obase + col] = x;
+            if (e.out_hi) {
+              bf16 h, l;
+              split_bf16(x, h, l);
+              e.out_hi[obase + col] = h;
+              if (e.out_lo) e.out_lo[obase + col] = l;
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT debug kernel: same operands (hi + lo re-joined to fp32), same epilogue, plain FMA.  Used to bisect
+// the tensor-core path on the GPU box (alm_set_option "gemm_impl" 1); never the default.
+// ------------------------------------------------------------------------------------------------
+struct SimtOperand {
+  const bf16* hi; const bf16* lo; long ld, bs0, bs1;
+};
+
+__global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int nsplit) {
+  __shared__ float sa[16][17];
+  __shared__ float sb[16][17];
+  const int batch = blockIdx.z;
+  const int b0 = batch % p.nb0, b1 = batch / p.nb0;
+  const long aoff = (p.a_b0 ? b0 : 0) * A.bs0 + (p.a_b1 ? b1 : 0) * A.bs1;
+  const long boff = (p.b_b0 ? b0 : 0) * B.bs0 + (p.b_b1 ? b1 : 0) * B.bs1;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    const int ka = k0 + tx;
+    float va = 0.f, vb = 0.f;
+    if (row < p.M && ka < p.K) {
+      va = __bfloat162float(A.hi[aoff + row * A.ld + ka]);
+      if (nsplit == 3) va += __bfloat162float(A.lo[aoff + row * A.ld + ka]);
+    }
+    const int brow = blockIdx.x * 16 + ty;
+    if (brow < p.N && ka < p.K) {
+      vb = __bfloat162float(B.hi[boff + brow * B.ld + ka]);
+      if (nsplit == 3) vb += __bfloat162float(B.lo[boff + brow * B.ld + ka]);
+    }
+    sa[ty][tx] = va;
+    sb[ty][tx] = vb;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
+    __syncthreads();
+  }
+  if (row >= p.M || col >= p.N) return;
+  const Epilogue& e = p.e;
+  long orow = row;
+  if (e.out_map) orow = e.out_map[row];
+  if (orow < 0) return;
+  long rrow = orow;
+  if (e.resid_map) rrow = e.resid_map[row];
+  float x = acc * e.alpha;
+  if (e.bias) {
+    const float* bias = e.bias + static_cast<long>(b0) * e.bias_bs0;
+    x += (e.bias_mode == BIAS_ROW) ? bias[row] : bias[col];
+  }
+  if (e.act == ACT_GELU) x = gelu_erf(x);
+  else if (e.act == ACT_RELU) x = fmaxf(x, 0.f);
+  if (e.resid) x += e.resid[b0 * e.rbs0 + b1 * e.rbs1 + rrow * e.ldr + col];
+  const long o = b0 * e.obs0 + b1 * e.obs1 + orow * e.ldo + col;
+  if (e.out_f32) e.out_f32[o] = x;
+  if (e.out_hi) {
+    bf16 h, l;
+    split_bf16(x, h, l);
+    e.out_hi[o] = h;
+    if (e.out_lo) e.out_lo[o] = l;
+  }
+}
+
+CUtensorMap make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows) {
+  CUtensorMap tm;
+  ALM_REQUIRE(base != nullptr, ALM_ERR_INVALID, "gemm operand pointer is null");
+  ALM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, ALM_ERR_INVALID, "gemm operand not 16-byte aligned");
+  ALM_REQUIRE(op.ld % 8 == 0 && op.bs0 % 8 == 0 && op.bs1 % 8 == 0, ALM_ERR_INVALID,
+              "gemm operand strides must be multiples of 8 elements");
+  cuuint64_t dims[4] = {cuuint64_t(op.K), cuuint64_t(op.rows), cuuint64_t(op.nb0), cuuint64_t(op.nb1)};
+  const cuuint64_t row_bytes = cuuint64_t(op.ld) * 2;
+  cuuint64_t s1 = op.nb0 > 1 ? cuuint64_t(op.bs0) * 2 : row_bytes * cuuint64_t(op.rows);
+  cuuint64_t s2 = op.nb1 > 1 ? cuuint64_t(op.bs1) * 2 : s1 * cuuint64_t(op.nb0);
+  if (s1 == 0) s1 = row_bytes;  // degenerate broadcast dims still need a legal stride
+  if (s2 == 0) s2 = s1;
+  cuuint64_t strides[3] = {row_bytes, s1, s2};
+  cuuint32_t box[4] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw AlmError{ALM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)) +
+                                     " (K=" + std::to_string(op.K) + " rows=" + std::to_string(op.rows) +
+                                     " ld=" + std::to_string(op.ld) + ")"};
+  return tm;
+}
+
+template <int BLOCK_N, int NSPLIT>
+void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
+  using L = SmemLayout<BLOCK_N, NSPLIT>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, NSPLIT>;
+  if (!attr_set) {
+    ALM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  p.n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  p.num_tiles = static_cast<long>(p.m_blocks) * p.n_blocks * p.nb0 * p.nb1;
+  CUtensorMap ta_hi = make_tmap(c, A.hi, A, BLOCK_M);
+  CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N);
+  CUtensorMap ta_lo = ta_hi, tb_lo = tb_hi;
+  if (NSPLIT == 3) {
+    ta_lo = make_tmap(c, A.lo, A, BLOCK_M);
+    tb_lo = make_tmap(c, B.lo, B, BLOCK_N);
+  }
+  const int grid = static_cast<int>(std::min<long>(p.num_tiles, c->num_sms));
+  kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+}
+
+}  // namespace
+
+void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
+  ALM_REQUIRE(A.K == B.K, ALM_ERR_INVALID, "gemm: K mismatch");
+  ALM_REQUIRE(A.rows > 0 && B.rows > 0 && A.K > 0, ALM_ERR_INVALID, "gemm: empty problem");
+  ALM_REQUIRE(E.out_f32 || E.out_hi, ALM_ERR_INVALID, "gemm: no output");
+  GemmParams p;
+  p.M = A.rows; p.N = B.rows; p.K = A.K;
+  p.nb0 = std::max(A.nb0, B.nb0);
+  p.nb1 = std::max(A.nb1, B.nb1);
+  ALM_REQUIRE((A.nb0 == 1 || A.nb0 == p.nb0) && (B.nb0 == 1 || B.nb0 == p.nb0) && (A.nb1 == 1 || A.nb1 == p.nb1) &&
+                  (B.nb1 == 1 || B.nb1 == p.nb1), ALM_ERR_INVALID, "gemm: batch extents do not broadcast");
+  ALM_REQUIRE(!(E.out_map || E.resid_map) || (p.nb0 == 1 && p.nb1 == 1), ALM_ERR_INVALID,
+              "gemm: row maps require an unbatched problem");
+  p.a_b0 = A.nb0 > 1; p.a_b1 = A.nb1 > 1; p.b_b0 = B.nb0 > 1; p.b_b1 = B.nb1 > 1;
+  p.m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  p.e = E;
+  bool vec = (E.ldo % 8 == 0) && (E.obs0 % 8 == 0) && (E.obs1 % 8 == 0);
+  if (E.out_f32) vec = vec && (reinterpret_cast<uintptr_t>(E.out_f32) % 16 == 0);
+  if (E.out_hi) vec = vec && (reinterpret_cast<uintptr_t>(E.out_hi) % 16 == 0);
+  if (E.out_lo) vec = vec && (reinterpret_cast<uintptr_t>(E.out_lo) % 16 == 0);
+  if (E.resid) vec = vec && (E.ldr % 4 == 0) && (E.rbs0 % 4 == 0) && (E.rbs1 % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(E.resid) % 16 == 0);
+  if (E.bias && E.bias_mode == BIAS_COL) vec = vec && (reinterpret_cast<uintptr_t>(E.bias) % 16 == 0) && (E.bias_bs0 % 4 == 0);
+  p.vec_ok = vec ? 1 : 0;
+  const int nsplit = c->nsplit;
+  ALM_REQUIRE(nsplit == 1 || (A.lo && B.lo), ALM_ERR_INVALID, "gemm: split mode needs lo operands");
+
+  if (c->gemm_impl == 1) {
+    p.n_blocks = 0; p.num_tiles = 0;
+    SimtOperand sa{A.hi, A.lo, A.ld, A.bs0, A.bs1}, sb{B.hi, B.lo, B.ld, B.bs0, B.bs1};
+    dim3 grid((p.N + 15) / 16, (p.M + 15) / 16, p.nb0 * p.nb1);
+    gemm_simt_kernel<<<grid, dim3(16, 16), 0, c->stream>>>(sa, sb, p, nsplit);
+  } else {
+    if (nsplit == 3) launch_tc<128, 3>(c, A, B, p);
+    else launch_tc<128, 1>(c, A, B, p);
+  }
+  count_launch(c);
+  check_launch("gemm");
+}
+
+}  // namespace alm

@@ -1,0 +1,350 @@
+// Non-GEMM kernels of the encoder path: patch im2col, gather + LayerNorm + operand split, Swin window
+// attention core, row softmax.  All are HBM-/latency-bound: vectorised 16-byte accesses, one warp per row.
+#include "alm_internal.h"
+#include "ptx.cuh"
+
+namespace alm {
+
+void count_launch(Ctx* c, int n) { c->launches += n; }
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw AlmError{ALM_ERR_CUDA, std::string("launch of ") + what + ": " + cudaGetErrorString(e)};
+}
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, long off, const float4& y) {
+  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(y.x, h0, l0); split_bf16(y.y, h1, l1); split_bf16(y.z, h2, l2); split_bf16(y.w, h3, l3);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather + LayerNorm + split.  One warp per output row; lane holds NV float4 (C = 128*NV).
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict__ map, int nsrc, int Cs, long rows,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int zero_missing,
+                 const float* __restrict__ add, long ld_add, float* __restrict__ out_f32, long ldo_f32,
+                 bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, long ldo_bf, bf16* __restrict__ out2_hi,
+                 bf16* __restrict__ out2_lo) {
+  const long r = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int C = NV * 128;
+  float4 v[NV];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int e = 4 * (lane + 32 * j);
+    const int s = e / Cs;
+    const long sr = map ? map[r * nsrc + s] : r * nsrc + s;
+    if (sr >= 0) {
+      v[j] = *reinterpret_cast<const float4*>(src + sr * lds + (e - s * Cs));
+      any = true;
+    } else {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const bool dead = zero_missing && !__any_sync(0xffffffffu, any);
+  if (gamma && !dead) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int e = 4 * (lane + 32 * j);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + e);
+      const float4 b = *reinterpret_cast<const float4*>(beta + e);
+      v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
+      v[j].y = (v[j].y - mean) * rstd * g.y + b.y;
+      v[j].z = (v[j].z - mean) * rstd * g.z + b.z;
+      v[j].w = (v[j].w - mean) * rstd * g.w + b.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int e = 4 * (lane + 32 * j);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ldo_f32 + e) = v[j];
+    if (out_hi) store_split4(out_hi, out_lo, r * ldo_bf + e, v[j]);
+    if (out2_hi) {
+      float4 y = v[j];
+      if (add) {
+        const float4 a = *reinterpret_cast<const float4*>(add + r * ld_add + e);
+        y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
+      }
+      store_split4(out2_hi, out2_lo, r * ldo_bf + e, y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4x4 / stride-4 patch im2col of an NCHW fp32 image into a K-major [B*Hp*Wp, 64] split operand
+// (k = c*16 + ky*4 + kx, columns 48..63 zero).  One thread per (patch, c, ky) -> one float4 of pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_patch4_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp,
+                                     bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * Hp * Wp * 16;
+  if (idx >= total) return;
+  const int q = static_cast<int>(idx & 15);
+  const long patch = idx >> 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < 12) {
+    const int c = q >> 2, ky = q & 3;
+    const int pw = static_cast<int>(patch % Wp);
+    const int ph = static_cast<int>((patch / Wp) % Hp);
+    const int b = static_cast<int>(patch / (static_cast<long>(Wp) * Hp));
+    const int y = 4 * ph + ky, x = 4 * pw;
+    if (y < H) {
+      const float* p = img + ((static_cast<long>(b) * 3 + c) * H + y) * W + x;
+      if (x + 3 < W && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        v = *reinterpret_cast<const float4*>(p);
+      } else {
+        if (x < W) v.x = p[0];
+        if (x + 1 < W) v.y = p[1];
+        if (x + 2 < W) v.z = p[2];
+        if (x + 3 < W) v.w = p[3];
+      }
+    }
+  }
+  store_split4(hi, lo, patch * 64 + q * 4, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Swin W-MSA core (swin_transformer.py:127-148): one CTA per (window, head), thread i = query token i.
+// scores = (q*scale) k^T + rel-pos bias + shift mask(-100) ; softmax ; P V.   fp32 FMA, K/V/bias in smem.
+// ---------------------------------------------------------------------------------------------
+constexpr int WT = 49;  // tokens per window
+constexpr int HD = 32;  // head dim (all Swin-B stages)
+
+__global__ void __launch_bounds__(64)
+window_attention_kernel(const float* __restrict__ qkv, int C, int nWh, int nWw, int shift, int Hp, int Wp,
+                        const float* __restrict__ bias_dense, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                        float* __restrict__ out_f32) {
+  __shared__ __align__(16) float sk[WT][HD];
+  __shared__ __align__(16) float sv[WT][HD];
+  __shared__ float sbias[WT * WT];
+  __shared__ int sreg[WT];
+  const int win = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+  const long row0 = static_cast<long>(win) * WT;
+  const int ld = 3 * C;
+  for (int i = t; i < WT * 8; i += 64) {
+    const int r = i >> 3, c4 = (i & 7) * 4;
+    const float* base = qkv + (row0 + r) * ld + h * HD + c4;
+    *reinterpret_cast<float4*>(&sk[r][c4]) = *reinterpret_cast<const float4*>(base + C);
+    *reinterpret_cast<float4*>(&sv[r][c4]) = *reinterpret_cast<const float4*>(base + 2 * C);
+  }
+  const float* bh = bias_dense + static_cast<long>(h) * WT * WT;
+  for (int i = t; i < WT * WT; i += 64) sbias[i] = bh[i];
+  if (t < WT) {
+    int reg = 0;
+    if (shift > 0) {
+      const int wi = win % (nWh * nWw);
+      const int hh = (wi / nWw) * 7 + t / 7, ww = (wi % nWw) * 7 + t % 7;
+      const int rh = hh < Hp - 7 ? 0 : (hh < Hp - shift ? 1 : 2);
+      const int rw = ww < Wp - 7 ? 0 : (ww < Wp - shift ? 1 : 2);
+      reg = rh * 3 + rw;
+    }
+    sreg[t] = reg;
+  }
+  __syncthreads();
+  if (t >= WT) return;
+
+  float q[HD];
+  {
+    const float scale = 0.17677669529663687f;  // 32 ** -0.5
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (row0 + t) * ld + h * HD);
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      const float4 x = qp[d];
+      q[4 * d] = x.x * scale; q[4 * d + 1] = x.y * scale; q[4 * d + 2] = x.z * scale; q[4 * d + 3] = x.w * scale;
+    }
+  }
+  const int myreg = sreg[t];
+  float s[WT];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[j][d]);
+      a = fmaf(q[d], kk.x, a); a = fmaf(q[d + 1], kk.y, a); a = fmaf(q[d + 2], kk.z, a); a = fmaf(q[d + 3], kk.w, a);
+    }
+    a += sbias[t * WT + j];
+    if (shift > 0 && sreg[j] != myreg) a += -100.0f;
+    s[j] = a;
+    m = fmaxf(m, a);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    s[j] = expf(s[j] - m);
+    sum += s[j];
+  }
+  float o[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < WT; ++j) {
+    const float pj = s[j] / sum;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
+      o[d] = fmaf(pj, vv.x, o[d]); o[d + 1] = fmaf(pj, vv.y, o[d + 1]);
+      o[d + 2] = fmaf(pj, vv.z, o[d + 2]); o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
+    }
+  }
+  const long ooff = (row0 + t) * C + h * HD;
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 y = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+    if (out_hi) store_split4(out_hi, out_lo, ooff + d, y);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + ooff + d) = y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> split bf16 rows (C multiple of 4)
+// ---------------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ src, long lds, long rows, int C, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo, long ldo) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c4 = C >> 2;
+  if (i >= rows * c4) return;
+  const long r = i / c4;
+  const int e = static_cast<int>(i % c4) * 4;
+  store_split4(hi, lo, r * ldo + e, *reinterpret_cast<const float4*>(src + r * lds + e));
+}
+
+// ---------------------------------------------------------------------------------------------
+// row softmax over n columns with optional key-padding mask (1 = -inf).  One CTA (128 threads) per row,
+// three passes over an L1/L2-resident row.  Output fp32 and/or split bf16 (columns n..ldo-1 untouched).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+softmax_rows_kernel(const float* __restrict__ s, long lds, int n, const uint8_t* __restrict__ kpm, int rows_per_mask,
+                    long mask_ld, float* __restrict__ out_f32, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                    long ldo) {
+  __shared__ float red[4];
+  const long r = blockIdx.x;
+  const float* x = s + r * lds;
+  const uint8_t* mk = kpm ? kpm + (r / rows_per_mask) * mask_ld : nullptr;
+  const int t = threadIdx.x;
+  float m = -INFINITY;
+  for (int j = t; j < n; j += 128) {
+    const float v = (mk && mk[j]) ? -INFINITY : x[j];
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  if ((t & 31) == 0) red[t >> 5] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = t; j < n; j += 128) {
+    const float v = (mk && mk[j]) ? -INFINITY : x[j];
+    sum += expf(v - m);
+  }
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  sum = (red[0] + red[1]) + (red[2] + red[3]);
+  for (int j = t; j < n; j += 128) {
+    const float v = (mk && mk[j]) ? -INFINITY : x[j];
+    const float p = expf(v - m) / sum;
+    if (out_f32) out_f32[r * ldo + j] = p;
+    if (out_hi) {
+      bf16 h, l;
+      split_bf16(p, h, l);
+      out_hi[r * ldo + j] = h;
+      if (out_lo) out_lo[r * ldo + j] = l;
+    }
+  }
+}
+
+}  // namespace
+
+void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int Cs, long rows, const float* gamma,
+               const float* beta, float eps, bool zero_missing, const float* add, long ld_add, float* out_f32,
+               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo) {
+  if (rows == 0) return;
+  const int C = nsrc * Cs;
+  ALM_REQUIRE(C % 128 == 0 && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID, "gather_ln: width must be a multiple of 128");
+  const int nv = C / 128;
+  const int wpb = 8;
+  dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb)), block(wpb * 32);
+#define ALM_GLN(NVV)                                                                                              \
+  case NVV:                                                                                                       \
+    gather_ln_kernel<NVV><<<grid, block, 0, c->stream>>>(src, lds, map, nsrc, Cs, rows, gamma, beta, eps,         \
+                                                         zero_missing ? 1 : 0, add, ld_add, out_f32, ldo_f32,     \
+                                                         out_hi, out_lo, ldo_bf, out2_hi, out2_lo);               \
+    break;
+  switch (nv) {
+    ALM_GLN(1) ALM_GLN(2) ALM_GLN(3) ALM_GLN(4) ALM_GLN(6) ALM_GLN(8) ALM_GLN(16)
+    default:
+      throw AlmError{ALM_ERR_UNSUPPORTED, "gather_ln: unsupported width " + std::to_string(C)};
+  }
+#undef ALM_GLN
+  count_launch(c);
+  check_launch("gather_ln");
+}
+
+void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp, bf16* hi, bf16* lo) {
+  const long total = static_cast<long>(B) * Hp * Wp * 16;
+  im2col_patch4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(img, B, H, W, Hp, Wp, hi, lo);
+  count_launch(c);
+  check_launch("im2col_patch4");
+}
+
+void window_attention(Ctx* c, const float* qkv, int C, int heads, int nWh, int nWw, int B, int shift, int Hp, int Wp,
+                      const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32) {
+  ALM_REQUIRE(C == heads * HD, ALM_ERR_UNSUPPORTED, "window_attention: head_dim must be 32");
+  dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
+  window_attention_kernel<<<grid, 64, 0, c->stream>>>(qkv, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi, out_lo,
+                                                      out_f32);
+  count_launch(c);
+  check_launch("window_attention");
+}
+
+void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo) {
+  ALM_REQUIRE(C % 4 == 0 && lds % 4 == 0 && ldo % 4 == 0, ALM_ERR_INVALID, "split_rows: width must be a multiple of 4");
+  const long total = rows * (C / 4);
+  if (total == 0) return;
+  split_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(src, lds, rows, C, hi, lo, ldo);
+  count_launch(c);
+  check_launch("split_rows");
+}
+
+void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint8_t* kpm, int rows_per_mask,
+                  long mask_ld, float* out_f32, bf16* out_hi, bf16* out_lo, long ldo) {
+  if (rows == 0) return;
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 128, 0, c->stream>>>(s, lds, n, kpm, rows_per_mask, mask_ld,
+                                                                          out_f32, out_hi, out_lo, ldo);
+  count_launch(c);
+  check_launch("softmax_rows");
+}
+
+}  // namespace alm

@@ -1,0 +1,11 @@
+// MGP-STR (ViT recogniser + A^3 heads) model state and entry points.
+#pragma once
+#include "alm_internal.h"
+
+namespace alm {
+struct MgpModel;
+void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& t);
+void mgp_forward(Ctx* c, const float* img_dev, int B, float* attn, float* char_logits, float* bpe_logits,
+                 float* wp_logits, int32_t* ids, float* prob);
+void mgp_free(MgpModel* m);
+}  // namespace alm

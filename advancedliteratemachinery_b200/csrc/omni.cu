@@ -1,0 +1,577 @@
+// OmniParser forward on the GPU: Swin-B encoder -> FPN -> input_proj -> three KV-cached point-conditioned
+// decoders.  This file is the host-side graph (sequence of kernel launches on the context stream); the
+// arithmetic lives in gemm.cu / kernels.cu / omni_kernels.cu.
+//
+// Reference being replaced (relative to /root/reference/OCR/OmniParser/):
+//   model/omniparser.py:19-32, model/backbone/swin_transformer.py:597-625, model/fpn.py:21-45,
+//   model/backbone/position_embedding.py:24-44, model/transformer.py:74-141,219-286.
+#include <math.h>
+
+#include <algorithm>
+
+#include "omni.h"
+
+namespace alm {
+
+SplitW upload_split(Ctx* c, const float* w, int N, int K, int Kpad);
+
+namespace {
+
+const int kDepths[4] = {2, 2, 18, 2};
+const int kHeads[4] = {4, 8, 16, 32};
+
+LNW load_ln(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int dim) {
+  const HostTensor& g = need(t, p + ".weight");
+  const HostTensor& b = need(t, p + ".bias");
+  ALM_REQUIRE(static_cast<int>(g.numel()) == dim && static_cast<int>(b.numel()) == dim, ALM_ERR_INVALID,
+              "LayerNorm shape mismatch at " + p);
+  LNW l;
+  l.g = upload_f32(c, g.f32.data(), dim);
+  l.b = upload_f32(c, b.f32.data(), dim);
+  return l;
+}
+
+Lin load_lin(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int N, int K, bool bias = true,
+             int Kpad = 0) {
+  const HostTensor& w = need(t, p + ".weight");
+  ALM_REQUIRE(static_cast<long>(w.numel()) == static_cast<long>(N) * K, ALM_ERR_INVALID,
+              "Linear weight shape mismatch at " + p);
+  Lin l;
+  l.w = upload_split(c, w.f32.data(), N, K, Kpad);
+  if (bias) {
+    const HostTensor& b = need(t, p + ".bias");
+    ALM_REQUIRE(static_cast<int>(b.numel()) == N, ALM_ERR_INVALID, "Linear bias shape mismatch at " + p);
+    l.b = upload_f32(c, b.f32.data(), N);
+  }
+  return l;
+}
+
+// rows [r0, r0+n) of a packed in_proj weight/bias
+Lin load_inproj_rows(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int r0, int n) {
+  const HostTensor& w = need(t, p + ".in_proj_weight");
+  const HostTensor& b = need(t, p + ".in_proj_bias");
+  ALM_REQUIRE(w.numel() == size_t(1536) * 512 && b.numel() == 1536, ALM_ERR_INVALID, "in_proj shape mismatch at " + p);
+  Lin l;
+  l.w = upload_split(c, w.f32.data() + static_cast<size_t>(r0) * 512, n, 512, 0);
+  l.b = upload_f32(c, b.f32.data() + r0, n);
+  return l;
+}
+
+Operand act_op(const bf16* hi, const bf16* lo, long rows, int K, long ld) {
+  Operand o;
+  o.hi = hi; o.lo = lo; o.rows = static_cast<int>(rows); o.K = K; o.ld = ld;
+  return o;
+}
+
+struct SplitBuf {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+};
+SplitBuf alloc_split(Ctx* c, size_t n) {
+  SplitBuf s;
+  s.hi = c->ws.get<bf16>(n);
+  s.lo = c->ws.get<bf16>(n);
+  return s;
+}
+
+void linear(Ctx* c, const SplitBuf& a, long rows, const Lin& l, int act, float* out_f32, SplitBuf* out_split,
+            const float* resid = nullptr, const int* out_map = nullptr, const int* resid_map = nullptr, long ldr = 0) {
+  Epilogue e;
+  e.out_f32 = out_f32;
+  if (out_split) { e.out_hi = out_split->hi; e.out_lo = out_split->lo; }
+  e.ldo = l.w.N;
+  e.bias = l.b;
+  e.bias_mode = l.b ? BIAS_COL : BIAS_NONE;
+  e.act = act;
+  e.resid = resid;
+  e.ldr = ldr ? ldr : l.w.N;
+  e.out_map = out_map;
+  e.resid_map = resid_map;
+  gemm(c, act_op(a.hi, a.lo, rows, l.w.K, l.w.K), l.w.op(), e);
+}
+
+}  // namespace
+
+// ================================================================================================ load
+void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
+  OmniModel* m = new OmniModel();
+  const std::string bb = "backbone.0.";
+  m->patch = load_lin(c, t, bb + "patch_embed.proj", 128, 48, true, 64);
+  m->patch_norm = load_ln(c, t, bb + "patch_embed.norm", 128);
+  // relative_position_index [49,49] (swin_transformer.py:98-109): recomputed, then cross-checked if present
+  std::vector<int> rel_index(49 * 49);
+  for (int i = 0; i < 49; ++i)
+    for (int j = 0; j < 49; ++j)
+      rel_index[i * 49 + j] = (i / 7 - j / 7 + 6) * 13 + (i % 7 - j % 7 + 6);
+  for (int s = 0; s < 4; ++s) {
+    const int C = 128 << s, heads = kHeads[s];
+    m->stage[s].blocks.resize(kDepths[s]);
+    for (int b = 0; b < kDepths[s]; ++b) {
+      const std::string p = bb + "layers." + std::to_string(s) + ".blocks." + std::to_string(b) + ".";
+      SwinBlockW& w = m->stage[s].blocks[b];
+      w.n1 = load_ln(c, t, p + "norm1", C);
+      w.n2 = load_ln(c, t, p + "norm2", C);
+      w.qkv = load_lin(c, t, p + "attn.qkv", 3 * C, C);
+      w.proj = load_lin(c, t, p + "attn.proj", C, C);
+      w.fc1 = load_lin(c, t, p + "mlp.fc1", 4 * C, C);
+      w.fc2 = load_lin(c, t, p + "mlp.fc2", C, 4 * C);
+      const HostTensor& tab = need(t, p + "attn.relative_position_bias_table");
+      ALM_REQUIRE(static_cast<int>(tab.numel()) == 169 * heads, ALM_ERR_INVALID, "bias table shape mismatch at " + p);
+      auto it = t.find(p + "attn.relative_position_index");
+      if (it != t.end()) {
+        ALM_REQUIRE(it->second.numel() == 49 * 49, ALM_ERR_INVALID, "relative_position_index shape at " + p);
+        for (int i = 0; i < 49 * 49; ++i)
+          ALM_REQUIRE(static_cast<int>(it->second.f32[i]) == rel_index[i], ALM_ERR_INVALID,
+                      "relative_position_index differs from the Swin definition at " + p);
+      }
+      std::vector<float> dense(static_cast<size_t>(heads) * 49 * 49);
+      for (int h = 0; h < heads; ++h)
+        for (int i = 0; i < 49 * 49; ++i) dense[static_cast<size_t>(h) * 2401 + i] = tab.f32[rel_index[i] * heads + h];
+      w.bias_dense = upload_f32(c, dense.data(), dense.size());
+    }
+    m->stage[s].out_norm = load_ln(c, t, bb + "norm" + std::to_string(s), C);
+    if (s < 3) {
+      const std::string p = bb + "layers." + std::to_string(s) + ".downsample.";
+      m->stage[s].merge_norm = load_ln(c, t, p + "norm", 4 * C);
+      m->stage[s].merge_red = load_lin(c, t, p + "reduction", 2 * C, 4 * C, false).w;
+    }
+  }
+  const int fpn_in[4] = {1024, 512, 256, 128};
+  for (int i = 0; i < 4; ++i) m->fpn[i] = load_lin(c, t, "fpn.fpn_in." + std::to_string(i), 256, fpn_in[i], false).w;
+  m->inproj = load_lin(c, t, "input_proj", 512, 1024);
+  {
+    std::vector<float> dt(256);
+    for (int i = 0; i < 256; ++i) dt[i] = powf(10000.0f, (2.0f * static_cast<float>(i / 2)) / 256.0f);
+    m->dim_t = upload_f32(c, dt.data(), 256);
+  }
+  // ---- decoder
+  const std::string tr = "transformer.";
+  const HostTensor& we = need(t, tr + "embedding.word_embeddings.weight");
+  ALM_REQUIRE(we.shape.size() == 2 && we.shape[1] == 512, ALM_ERR_INVALID, "word_embeddings shape");
+  m->V = static_cast<int>(we.shape[0]);
+  m->vie = m->V - 1104;
+  ALM_REQUIRE(m->vie >= 0, ALM_ERR_INVALID, "vocabulary smaller than the text-spotting layout (1104)");
+  ALM_REQUIRE(kind != ALM_MODEL_OMNI_SPOT || m->vie == 0, ALM_ERR_INVALID, "text-spotting checkpoint must have V = 1104");
+  m->word_emb = upload_f32(c, we.f32.data(), we.numel());
+  const char* kinds[3] = {"pt", "poly", "rec"};
+  for (int d = 0; d < 3; ++d) {
+    const HostTensor& pe = need(t, tr + "embedding." + kinds[d] + "_position_embeddings.weight");
+    ALM_REQUIRE(pe.numel() == size_t(1024) * 512, ALM_ERR_INVALID, "position embedding shape");
+    m->pos_emb[d] = upload_f32(c, pe.f32.data(), pe.numel());
+  }
+  m->emb_norm = load_ln(c, t, tr + "embedding.LayerNorm", 512);
+  std::vector<float> kw(size_t(12) * 512 * 512), kb(12 * 512), vw(size_t(12) * 512 * 512), vb(12 * 512);
+  for (int d = 0; d < 3; ++d) {
+    for (int l = 0; l < 4; ++l) {
+      const std::string p = tr + kinds[d] + "_decoder.layers." + std::to_string(l) + ".";
+      DecLayerW& w = m->dec[d][l];
+      w.n1 = load_ln(c, t, p + "norm1", 512);
+      w.n2 = load_ln(c, t, p + "norm2", 512);
+      w.n3 = load_ln(c, t, p + "norm3", 512);
+      w.sa_qk = load_inproj_rows(c, t, p + "self_attn", 0, 1024);
+      w.sa_v = load_inproj_rows(c, t, p + "self_attn", 1024, 512);
+      w.sa_out = load_lin(c, t, p + "self_attn.out_proj", 512, 512);
+      w.ca_q = load_inproj_rows(c, t, p + "multihead_attn", 0, 512);
+      w.ca_out = load_lin(c, t, p + "multihead_attn.out_proj", 512, 512);
+      w.l1 = load_lin(c, t, p + "linear1", 2048, 512);
+      w.l2 = load_lin(c, t, p + "linear2", 512, 2048);
+      const HostTensor& ipw = need(t, p + "multihead_attn.in_proj_weight");
+      const HostTensor& ipb = need(t, p + "multihead_attn.in_proj_bias");
+      const size_t dl = static_cast<size_t>(d) * 4 + l;
+      std::copy(ipw.f32.begin() + size_t(512) * 512, ipw.f32.begin() + size_t(1024) * 512, kw.begin() + dl * 512 * 512);
+      std::copy(ipw.f32.begin() + size_t(1024) * 512, ipw.f32.begin() + size_t(1536) * 512, vw.begin() + dl * 512 * 512);
+      std::copy(ipb.f32.begin() + 512, ipb.f32.begin() + 1024, kb.begin() + dl * 512);
+      std::copy(ipb.f32.begin() + 1024, ipb.f32.begin() + 1536, vb.begin() + dl * 512);
+    }
+    m->dec_norm[d] = load_ln(c, t, tr + kinds[d] + "_decoder.norm", 512);
+    const std::string hp = tr + kinds[d] + "_pred_layer.layers.";
+    m->head[d][0] = load_lin(c, t, hp + "0", 512, 512);
+    m->head[d][1] = load_lin(c, t, hp + "1", 512, 512);
+    m->head[d][2] = load_lin(c, t, hp + "2", m->V, 512);
+  }
+  m->ca_k_all.w = upload_split(c, kw.data(), 12 * 512, 512, 0);
+  m->ca_k_all.b = upload_f32(c, kb.data(), kb.size());
+  m->ca_v_all.w = upload_split(c, vw.data(), 12 * 512, 512, 0);
+  m->ca_v_all.b = upload_f32(c, vb.data(), vb.size());
+  delete c->omni;
+  c->omni = m;
+}
+
+// ================================================================================================ encode
+void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, int W) {
+  OmniModel* m = c->omni;
+  ALM_REQUIRE(m != nullptr, ALM_ERR_STATE, "alm_omni_encode before alm_load_weights");
+  ALM_REQUIRE(B > 0 && H >= 32 && W >= 32, ALM_ERR_INVALID, "image batch must be non-empty and at least 32x32");
+  c->ensure_ws();
+  Arena& ws = c->ws;
+  ws.off = 0;
+  m->encoded = false;
+  m->B = B; m->H = H; m->W = W;
+  int hs = (H + 3) / 4, wsz = (W + 3) / 4;
+  for (int s = 0; s < 4; ++s) {
+    m->Hs[s] = hs; m->Ws[s] = wsz;
+    hs = (hs + 1) / 2; wsz = (wsz + 1) / 2;
+  }
+  m->mh = m->Hs[2]; m->mw = m->Ws[2];
+  m->M = m->mh * m->mw;
+  m->Mpad = (m->M + 7) & ~7;
+  const long BM = static_cast<long>(B) * m->M;
+
+  // ---- encode-persistent buffers
+  for (int s = 0; s < 4; ++s) m->feat[s] = ws.get<float>(static_cast<size_t>(B) * m->Hs[s] * m->Ws[s] * (128 << s));
+  m->memory = ws.get<float>(BM * 512);
+  m->pos = ws.get<float>(BM * 512);
+  m->kpm = ws.get<uint8_t>(BM);
+  m->kc_hi = ws.get<bf16>(BM * 6144);
+  m->kc_lo = ws.get<bf16>(BM * 6144);
+  m->vt_hi = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
+  m->vt_lo = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
+  m->ws_mark = ws.mark();
+
+  // ---- patch embed: im2col -> GEMM(+bias) -> LN   (swin_transformer.py:427-443)
+  long rows = static_cast<long>(B) * m->Hs[0] * m->Ws[0];
+  float* x = ws.get<float>(rows * 128);
+  {
+    const size_t mk = ws.mark();
+    SplitBuf a = alloc_split(c, rows * 64);
+    float* tmp = ws.get<float>(rows * 128);
+    im2col_patch4(c, img, B, H, W, m->Hs[0], m->Ws[0], a.hi, a.lo);
+    linear(c, a, rows, m->patch, ACT_NONE, tmp, nullptr);
+    gather_ln(c, tmp, 128, nullptr, 1, 128, rows, m->patch_norm.g, m->patch_norm.b, 1e-5f, false, nullptr, 0, x, 128,
+              nullptr, nullptr, 0, nullptr, nullptr);
+    ws.release(mk);
+    // x was allocated before mk, tmp/a are dead after the LN (stream-ordered)
+  }
+
+  SplitBuf feat_split[4];
+  for (int s = 0; s < 4; ++s) {
+    const int C = 128 << s, heads = kHeads[s];
+    const int Hc = m->Hs[s], Wc = m->Ws[s];
+    const int nWh = (Hc + 6) / 7, nWw = (Wc + 6) / 7;
+    const long rowsP = static_cast<long>(B) * nWh * nWw * 49;
+    rows = static_cast<long>(B) * Hc * Wc;
+    const size_t stage_mark = ws.mark();
+    int* map0 = ws.get<int>(rowsP);
+    int* map1 = ws.get<int>(rowsP);
+    window_map(c, map0, B, Hc, Wc, nWh, nWw, 0);
+    window_map(c, map1, B, Hc, Wc, nWh, nWw, 3);
+    SplitBuf lnw = alloc_split(c, std::max(rowsP, rows) * C);
+    float* qkv = ws.get<float>(rowsP * 3 * C);
+    SplitBuf att = alloc_split(c, rowsP * C);
+    SplitBuf hid = alloc_split(c, rows * 4 * C);
+    for (int b = 0; b < kDepths[s]; ++b) {
+      const SwinBlockW& w = m->stage[s].blocks[b];
+      const int shift = (b & 1) ? 3 : 0;
+      const int* map = shift ? map1 : map0;
+      // LN1 -> zero-pad -> roll -> window partition, as one gather (pad tokens stay live keys, F10)
+      gather_ln(c, x, C, map, 1, C, rowsP, w.n1.g, w.n1.b, 1e-5f, true, nullptr, 0, nullptr, 0, lnw.hi, lnw.lo, C,
+                nullptr, nullptr);
+      linear(c, lnw, rowsP, w.qkv, ACT_NONE, qkv, nullptr);
+      window_attention(c, qkv, C, heads, nWh, nWw, B, shift, nWh * 7, nWw * 7, w.bias_dense, att.hi, att.lo, nullptr);
+      // proj + window reverse + un-roll + crop + residual, fused in the GEMM epilogue (scatter map)
+      linear(c, att, rowsP, w.proj, ACT_NONE, x, nullptr, x, map, nullptr, C);
+      gather_ln(c, x, C, nullptr, 1, C, rows, w.n2.g, w.n2.b, 1e-5f, false, nullptr, 0, nullptr, 0, lnw.hi, lnw.lo, C,
+                nullptr, nullptr);
+      linear(c, lnw, rows, w.fc1, ACT_GELU, nullptr, &hid);
+      linear(c, hid, rows, w.fc2, ACT_NONE, x, nullptr, x, nullptr, nullptr, C);
+    }
+    ws.release(stage_mark);
+    // per-stage output norm (swin_transformer.py:616-618): fp32 feature (API) + split operand (FPN)
+    feat_split[s] = alloc_split(c, rows * C);
+    gather_ln(c, x, C, nullptr, 1, C, rows, m->stage[s].out_norm.g, m->stage[s].out_norm.b, 1e-5f, false, nullptr, 0,
+              m->feat[s], C, feat_split[s].hi, feat_split[s].lo, C, nullptr, nullptr);
+    if (s < 3) {
+      // PatchMerging: 2x2 gather-concat -> LN(4C) -> Linear 4C->2C (swin_transformer.py:269-296)
+      const int H2 = m->Hs[s + 1], W2 = m->Ws[s + 1];
+      const long rows2 = static_cast<long>(B) * H2 * W2;
+      float* xn = ws.get<float>(rows2 * 2 * C);
+      const size_t mk = ws.mark();
+      int* mm = ws.get<int>(rows2 * 4);
+      SplitBuf ma = alloc_split(c, rows2 * 4 * C);
+      merge_map(c, mm, B, Hc, Wc, H2, W2);
+      gather_ln(c, x, C, mm, 4, C, rows2, m->stage[s].merge_norm.g, m->stage[s].merge_norm.b, 1e-5f, false, nullptr, 0,
+                nullptr, 0, ma.hi, ma.lo, 4 * C, nullptr, nullptr);
+      Lin red;
+      red.w = m->stage[s].merge_red;
+      linear(c, ma, rows2, red, ACT_NONE, xn, nullptr);
+      ws.release(mk);
+      x = xn;
+    }
+  }
+
+  // ---- FPN (fpn.py:21-45): p5, p4 = c4' + up(p5), p3, p2 at full resolution, fp32
+  float* p[4];  // p[0]=p2 (stage 0 res) ... p[3]=p5
+  for (int s = 0; s < 4; ++s) p[s] = ws.get<float>(static_cast<size_t>(B) * m->Hs[s] * m->Ws[s] * 256);
+  for (int s = 3; s >= 0; --s) {
+    rows = static_cast<long>(B) * m->Hs[s] * m->Ws[s];
+    Lin l;
+    l.w = m->fpn[3 - s];
+    if (s == 3) {
+      linear(c, feat_split[s], rows, l, ACT_NONE, p[s], nullptr);
+    } else {
+      const size_t mk = ws.mark();
+      int* up = ws.get<int>(rows);
+      nearest_map(c, up, B, m->Hs[s], m->Ws[s], m->Hs[s + 1], m->Ws[s + 1]);
+      linear(c, feat_split[s], rows, l, ACT_NONE, p[s], nullptr, p[s + 1], nullptr, up, 256);
+      ws.release(mk);  // map is consumed by the GEMM already enqueued; later allocations are stream-ordered after it
+    }
+  }
+  // consumer-side assembly of the stride-2-sampled concat + input_proj (omniparser.py:15,31)
+  SplitBuf cat = alloc_split(c, BM * 1024);
+  fpn_assemble(c, p[0], p[1], p[2], p[3], B, m->Hs, m->Ws, m->mh, m->mw, cat.hi, cat.lo);
+  linear(c, cat, BM, m->inproj, ACT_NONE, m->memory, nullptr);
+  sine_pos(c, mask, B, H, W, m->mh, m->mw, m->dim_t, m->pos, m->kpm);
+  // operands for the cross-attention K/V projections: memory and memory + pos
+  SplitBuf mem = alloc_split(c, BM * 512), memp = alloc_split(c, BM * 512);
+  gather_ln(c, m->memory, 512, nullptr, 1, 512, BM, nullptr, nullptr, 0.f, false, m->pos, 512, nullptr, 0, mem.hi,
+            mem.lo, 512, memp.hi, memp.lo);
+  {  // K_c[b*M + m, dl*512 + f] = (memory + pos) Wk^T + bk for all 12 (decoder, layer) pairs at once
+    Epilogue e;
+    e.out_hi = m->kc_hi; e.out_lo = m->kc_lo; e.ldo = 6144;
+    e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL;
+    gemm(c, act_op(memp.hi, memp.lo, BM, 512, 512), m->ca_k_all.w.op(), e);
+  }
+  {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
+    Operand bop = act_op(mem.hi, mem.lo, m->M, 512, 512);
+    bop.nb1 = B; bop.bs1 = static_cast<long>(m->M) * 512;
+    Epilogue e;
+    e.out_hi = m->vt_hi; e.out_lo = m->vt_lo; e.ldo = m->Mpad; e.obs1 = static_cast<long>(6144) * m->Mpad;
+    e.bias = m->ca_v_all.b; e.bias_mode = BIAS_ROW;
+    gemm(c, m->ca_v_all.w.op(), bop, e);
+  }
+  ws.release(m->ws_mark);
+  m->encoded = true;
+}
+
+// ================================================================================================ decode
+namespace {
+
+struct DecodeBufs {
+  int S = 0, Tmax = 0, Ncap = 0;
+  float* x = nullptr;
+  SplitBuf ln, lnp, att, q, o, hid, h0, h1;
+  float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr;
+  SplitBuf prob;
+  float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* vc[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
+  DecodeBufs d;
+  d.S = B * Ncap; d.Tmax = Tmax; d.Ncap = Ncap;
+  const size_t S = d.S;
+  d.x = c->ws.get<float>(S * 512);
+  d.ln = alloc_split(c, S * 512);
+  d.lnp = alloc_split(c, S * 512);
+  d.att = alloc_split(c, S * 512);
+  d.q = alloc_split(c, S * 512);
+  d.o = alloc_split(c, S * 512);
+  d.hid = alloc_split(c, S * 2048);
+  d.h0 = alloc_split(c, S * 512);
+  d.h1 = alloc_split(c, S * 512);
+  d.qk = c->ws.get<float>(S * 1024);
+  d.v = c->ws.get<float>(S * 512);
+  d.scores = c->ws.get<float>(S * 8 * m->Mpad);
+  d.prob = alloc_split(c, S * 8 * m->Mpad);
+  d.logits = c->ws.get<float>(S * m->V);
+  for (int l = 0; l < 4; ++l) {
+    d.kc[l] = c->ws.get<float>(S * Tmax * 512);
+    d.vc[l] = c->ws.get<float>(S * Tmax * 512);
+  }
+  return d;
+}
+
+// One decoder pass over the token at position t of every sequence (pre-norm layer, transformer.py:430-454,
+// with self-attention K/V cached and the cross-attention K/V precomputed per image).
+// img0: first image of the batch slice the S sequences belong to; nimg images x Ncap sequences each.
+void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, int tstride, int t, int img0, int nimg,
+                  bool want_logits) {
+  const int S = u.S, Ncap = u.Ncap, M = m->M, Mpad = m->Mpad;
+  const float* qpos = m->pos_emb[d] + static_cast<long>(t) * 512;
+  embed_ln(c, tokens, tstride, t, S, m->word_emb, m->pos_emb[d], m->emb_norm.g, m->emb_norm.b, u.x);
+  for (int l = 0; l < 4; ++l) {
+    const DecLayerW& w = m->dec[d][l];
+    const long dl = static_cast<long>(d) * 4 + l;
+    // --- self attention
+    gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n1.g, w.n1.b, 1e-5f, false, qpos, 0, nullptr, 0, u.ln.hi, u.ln.lo, 512,
+              u.lnp.hi, u.lnp.lo);
+    linear(c, u.lnp, S, w.sa_qk, ACT_NONE, u.qk, nullptr);
+    linear(c, u.ln, S, w.sa_v, ACT_NONE, u.v, nullptr);
+    self_attn_step(c, u.qk, u.v, u.kc[l], u.vc[l], S, t, u.Tmax, u.att.hi, u.att.lo);
+    linear(c, u.att, S, w.sa_out, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
+    // --- cross attention against the per-image cached K / V^T
+    gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n2.g, w.n2.b, 1e-5f, false, qpos, 0, nullptr, 0, nullptr, nullptr, 512,
+              u.lnp.hi, u.lnp.lo);
+    linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
+    {
+      Operand a = act_op(u.q.hi, u.q.lo, Ncap, 64, 512);
+      a.nb0 = 8; a.bs0 = 64; a.nb1 = nimg; a.bs1 = static_cast<long>(Ncap) * 512;
+      const long koff = static_cast<long>(img0) * M * 6144 + dl * 512;
+      Operand k = act_op(m->kc_hi + koff, m->kc_lo + koff, M, 64, 6144);
+      k.nb0 = 8; k.bs0 = 64; k.nb1 = nimg; k.bs1 = static_cast<long>(M) * 6144;
+      Epilogue e;
+      e.out_f32 = u.scores; e.ldo = Mpad; e.obs0 = static_cast<long>(Ncap) * Mpad; e.obs1 = static_cast<long>(8) * Ncap * Mpad;
+      e.alpha = 0.125f;  // == scaling q by 64^-0.5 before q k^T (exact: power of two)
+      gemm(c, a, k, e);
+    }
+    softmax_rows(c, u.scores, Mpad, static_cast<long>(S) * 8, M, m->kpm + static_cast<long>(img0) * M, 8 * Ncap, M,
+                 nullptr, u.prob.hi, u.prob.lo, Mpad);
+    {
+      Operand a = act_op(u.prob.hi, u.prob.lo, Ncap, M, Mpad);
+      a.nb0 = 8; a.bs0 = static_cast<long>(Ncap) * Mpad; a.nb1 = nimg; a.bs1 = static_cast<long>(8) * Ncap * Mpad;
+      const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
+      Operand v = act_op(m->vt_hi + voff, m->vt_lo + voff, 64, M, Mpad);
+      v.nb0 = 8; v.bs0 = static_cast<long>(64) * Mpad; v.nb1 = nimg; v.bs1 = static_cast<long>(6144) * Mpad;
+      Epilogue e;
+      e.out_hi = u.o.hi; e.out_lo = u.o.lo; e.ldo = 512; e.obs0 = 64; e.obs1 = static_cast<long>(Ncap) * 512;
+      gemm(c, a, v, e);
+    }
+    linear(c, u.o, S, w.ca_out, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
+    // --- FFN
+    gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n3.g, w.n3.b, 1e-5f, false, nullptr, 0, nullptr, 0, u.ln.hi, u.ln.lo,
+              512, nullptr, nullptr);
+    linear(c, u.ln, S, w.l1, ACT_RELU, nullptr, &u.hid);
+    linear(c, u.hid, S, w.l2, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
+  }
+  if (!want_logits) return;
+  gather_ln(c, u.x, 512, nullptr, 1, 512, S, m->dec_norm[d].g, m->dec_norm[d].b, 1e-5f, false, nullptr, 0, nullptr, 0,
+            u.ln.hi, u.ln.lo, 512, nullptr, nullptr);
+  linear(c, u.ln, S, m->head[d][0], ACT_RELU, nullptr, &u.h0);
+  linear(c, u.h0, S, m->head[d][1], ACT_RELU, nullptr, &u.h1);
+  linear(c, u.h1, S, m->head[d][2], ACT_NONE, u.logits, nullptr);
+}
+
+}  // namespace
+
+void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
+                 int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
+  OmniModel* m = c->omni;
+  ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode before alm_omni_encode");
+  ALM_REQUIRE(n_prompt >= 1 && n_prompt <= 16, ALM_ERR_INVALID, "pt prompt length");
+  ALM_REQUIRE(cfg.pt_seq_length >= 1 && n_prompt + cfg.pt_seq_length - 1 <= 1024, ALM_ERR_INVALID,
+              "prompt + pt_seq_length exceeds the 1024-row position table (transformer.py:475)");
+  ALM_REQUIRE(cfg.vie_categories == 0 && m->vie == 0, ALM_ERR_UNSUPPORTED, "KIE decode is not built yet (SURVEY 8f-3)");
+  ALM_REQUIRE(cfg.max_instances >= (cfg.pt_seq_length / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
+  ALM_REQUIRE(cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
+  const int B = m->B;
+  Arena& ws = c->ws;
+  ws.release(m->ws_mark);
+  HeadCfg hc{cfg.num_bins, cfg.pt_eos, cfg.rec_eos, cfg.recog_pad, 0};
+
+  // ------------------------------------------------------------------ pt loop (transformer.py:102-141)
+  const int Tpt = n_prompt + cfg.pt_seq_length;
+  int* pt_tok = ws.get<int>(static_cast<size_t>(B) * Tpt);
+  int* finished = ws.get<int>(B);
+  int* ntok = ws.get<int>(B);
+  {
+    std::vector<int> h(static_cast<size_t>(B) * Tpt, 0);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < n_prompt; ++i) h[static_cast<size_t>(b) * Tpt + i] = static_cast<int>(pt_prompt[i]);
+    ALM_CHECK_CUDA(cudaMemcpyAsync(pt_tok, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));  // h goes out of scope
+  }
+  fill_i32(c, finished, B, 0);
+  fill_i32(c, ntok, B, 0);
+  const size_t after_pt_tokens = ws.mark();
+  {
+    DecodeBufs u = alloc_decode(c, m, B, 1, Tpt - 1);
+    std::vector<int> fin(B);
+    for (int t = 0; t < Tpt - 1; ++t) {
+      const int gen = t - (n_prompt - 1);
+      decoder_step(c, m, 0, u, pt_tok, Tpt, t, 0, B, gen >= 0);
+      if (gen >= 0) {
+        head_select(c, u.logits, B, m->V, m->V, (gen % 2 == 0) ? 0 : 1, hc, pt_tok, Tpt, t + 1, nullptr, 0, 0, finished,
+                    ntok, gen, 1);
+        if ((gen & 15) == 15 && t + 1 < Tpt - 1) {  // every image hit EOS?  (one small sync per 16 tokens)
+          ALM_CHECK_CUDA(cudaMemcpyAsync(fin.data(), finished, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+          ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+          if (std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; })) break;
+        }
+      }
+    }
+  }
+  std::vector<int> h_ntok(B);
+  ALM_CHECK_CUDA(cudaMemcpyAsync(h_ntok.data(), ntok, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  int Ncap = 0;
+  for (int b = 0; b < B; ++b) {
+    n_inst[b] = h_ntok[b] / 2;
+    Ncap = std::max(Ncap, h_ntok[b] / 2);
+  }
+  ALM_REQUIRE(Ncap <= cfg.max_instances, ALM_ERR_INVALID, "decoded more points than max_instances");
+  const int maxI = cfg.max_instances;
+  {  // pt output: [B, max_inst, 2]
+    std::vector<int> h(static_cast<size_t>(B) * Tpt);
+    ALM_CHECK_CUDA(cudaMemcpyAsync(h.data(), pt_tok, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b)
+      for (int n = 0; n < n_inst[b]; ++n)
+        for (int k = 0; k < 2; ++k)
+          pt[(static_cast<size_t>(b) * maxI + n) * 2 + k] = h[static_cast<size_t>(b) * Tpt + n_prompt + 2 * n + k];
+  }
+  if (Ncap == 0) return;
+
+  // ------------------------------------------------------------------ poly / rec loops (:249-284)
+  for (int phase = 1; phase <= 2; ++phase) {
+    ws.release(after_pt_tokens);
+    const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
+    const int T = 3 + len;
+    const int S = B * Ncap;
+    int* tok = ws.get<int>(static_cast<size_t>(S) * T);
+    float* probs = ws.get<float>(static_cast<size_t>(S) * len);
+    fill_i32(c, tok, static_cast<long>(S) * T, 0);
+    build_inst_prompts(c, pt_tok, Tpt, n_prompt, ntok, B, Ncap, phase == 1 ? cfg.poly_sos : cfg.rec_sos, tok, T);
+    DecodeBufs u = alloc_decode(c, m, B, Ncap, T - 1);
+    for (int t = 0; t < T - 1; ++t) {
+      const int gen = t - 2;
+      decoder_step(c, m, phase, u, tok, T, t, 0, B, gen >= 0);
+      if (gen >= 0)
+        head_select(c, u.logits, S, m->V, m->V, phase == 1 ? 1 : 2, hc, tok, T, t + 1, probs, len, gen, nullptr, nullptr,
+                    gen, Ncap);
+    }
+    std::vector<int> h(static_cast<size_t>(S) * T);
+    std::vector<float> hp(static_cast<size_t>(S) * len);
+    ALM_CHECK_CUDA(cudaMemcpyAsync(h.data(), tok, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaMemcpyAsync(hp.data(), probs, hp.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < B; ++b)
+      for (int n = 0; n < n_inst[b]; ++n) {
+        const size_t s = static_cast<size_t>(b) * Ncap + n;
+        for (int k = 0; k < len; ++k) {
+          const size_t o = (static_cast<size_t>(b) * maxI + n) * len + k;
+          if (phase == 1) poly[o] = h[s * T + 3 + k];
+          else { rec[o] = h[s * T + 3 + k]; rec_prob[o] = hp[s * len + k]; }
+        }
+      }
+  }
+  ws.release(m->ws_mark);
+}
+
+// Teacher-forced logits for one image: every position of every sequence (Transformer.decode, :74-100).
+void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
+  OmniModel* m = c->omni;
+  ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode_logits before alm_omni_encode");
+  ALM_REQUIRE(image >= 0 && image < m->B && kind >= 0 && kind < 3 && n_seq > 0 && len > 0 && len <= 1024,
+              ALM_ERR_INVALID, "decode_logits arguments");
+  Arena& ws = c->ws;
+  ws.release(m->ws_mark);
+  std::vector<int> h(static_cast<size_t>(n_seq) * len);
+  for (size_t i = 0; i < h.size(); ++i) {
+    ALM_REQUIRE(seq[i] >= 0 && seq[i] < m->V, ALM_ERR_INVALID, "token id out of range");
+    h[i] = static_cast<int>(seq[i]);
+  }
+  int* tok = ws.get<int>(h.size());
+  ALM_CHECK_CUDA(cudaMemcpyAsync(tok, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  DecodeBufs u = alloc_decode(c, m, 1, n_seq, len);
+  for (int t = 0; t < len; ++t) {
+    decoder_step(c, m, kind, u, tok, len, t, image, 1, true);
+    // logits [n_seq, len, V] <- step t rows
+    ALM_CHECK_CUDA(cudaMemcpy2DAsync(logits + static_cast<size_t>(t) * m->V, static_cast<size_t>(len) * m->V * sizeof(float),
+                                     u.logits, static_cast<size_t>(m->V) * sizeof(float), static_cast<size_t>(m->V) * sizeof(float),
+                                     n_seq, cudaMemcpyDeviceToHost, c->stream));
+  }
+  ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  ws.release(m->ws_mark);
+}
+
+}  // namespace alm

@@ -1,0 +1,99 @@
+// OmniParser model state (weights + per-batch encode/decode buffers) and kernel wrappers.
+#pragma once
+#include "alm_internal.h"
+
+namespace alm {
+
+struct HeadCfg {
+  int num_bins, pt_eos, rec_eos, recog_pad, vie;
+};
+
+struct LNW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct Lin {
+  SplitW w;
+  float* b = nullptr;
+};
+
+struct SwinBlockW {
+  LNW n1, n2;
+  Lin qkv, proj, fc1, fc2;
+  float* bias_dense = nullptr;  // [heads,49,49] = table[index]  (swin_transformer.py:133-135)
+};
+struct SwinStageW {
+  std::vector<SwinBlockW> blocks;
+  LNW out_norm;   // norm{s}
+  LNW merge_norm;  // downsample.norm
+  SplitW merge_red;
+};
+struct DecLayerW {
+  LNW n1, n2, n3;
+  Lin sa_qk;   // rows [0,1024) of self_attn.in_proj (q then k)
+  Lin sa_v;    // rows [1024,1536)
+  Lin sa_out;
+  Lin ca_q;    // rows [0,512) of multihead_attn.in_proj
+  Lin ca_out;
+  Lin l1, l2;
+};
+
+struct OmniModel {
+  int V = 0;
+  int vie = 0;
+  Lin patch;
+  LNW patch_norm;
+  SwinStageW stage[4];
+  SplitW fpn[4];  // fpn_in[0..3] : c5,c4,c3,c2
+  Lin inproj;
+  float* dim_t = nullptr;  // [256]
+  // decoder
+  float* word_emb = nullptr;
+  float* pos_emb[3] = {nullptr, nullptr, nullptr};  // pt, poly, rec
+  LNW emb_norm;
+  DecLayerW dec[3][4];
+  LNW dec_norm[3];
+  Lin ca_k_all;  // [12*512, 512]  rows (d*4+l)*512..: cross-attn K projections of all decoder layers
+  Lin ca_v_all;  // [12*512, 512]
+  Lin head[3][3];
+
+  // ---- state of the last alm_omni_encode -------------------------------------------------------
+  bool encoded = false;
+  int B = 0, H = 0, W = 0;
+  int Hs[4] = {0, 0, 0, 0}, Ws[4] = {0, 0, 0, 0};
+  int mh = 0, mw = 0, M = 0, Mpad = 0;
+  float* feat[4] = {nullptr, nullptr, nullptr, nullptr};  // LN'd stage outputs, NHWC fp32
+  float* memory = nullptr;                                // [B*M,512]
+  float* pos = nullptr;                                   // [B*M,512]
+  uint8_t* kpm = nullptr;                                 // [B*M]
+  bf16 *kc_hi = nullptr, *kc_lo = nullptr;                // [B*M, 6144]
+  bf16 *vt_hi = nullptr, *vt_lo = nullptr;                // [B, 6144, Mpad]
+  size_t ws_mark = 0;                                     // arena offset after the encode-persistent buffers
+};
+
+void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t);
+void omni_encode(Ctx* c, const float* img_dev, const uint8_t* mask_dev, int B, int H, int W);
+void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
+                 int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);
+void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits);
+
+// kernels (omni_kernels.cu)
+void window_map(Ctx* c, int* map, int B, int H, int W, int nWh, int nWw, int shift);
+void merge_map(Ctx* c, int* map, int B, int H, int W, int H2, int W2);
+void nearest_map(Ctx* c, int* map, int B, int Hd, int Wd, int Hs, int Ws);
+void fpn_assemble(Ctx* c, const float* p2, const float* p3, const float* p4, const float* p5, int B, const int* Hs,
+                  const int* Ws, int Ho, int Wo, bf16* hi, bf16* lo);
+void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, const float* dim_t, float* pos,
+              uint8_t* kpm);
+void embed_ln(Ctx* c, const int* tokens, int tstride, int t, int S, const float* word_emb, const float* pos_emb,
+              const float* gamma, const float* beta, float* x);
+void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, int t, int Tmax,
+                    bf16* out_hi, bf16* out_lo);
+void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int mode, const HeadCfg& cfg, int* tokens,
+                 int tstride, int tnext, float* probs, int pstride, int pidx, int* finished, int* ntok, int gen_index,
+                 int seqs_per_image);
+void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,
+                        int sos, int* tokens, int tstride);
+void fill_i32(Ctx* c, int* p, long n, int v);
+
+}  // namespace alm

@@ -1,0 +1,181 @@
+"""OmniParserB200: the reference's ``OmniParser.forward`` call site served by libalm_ocr.so.
+
+Reference boundary (relative to /root/reference/OCR/OmniParser/):
+  ``output = model(samples, seqs)``                      engine/val.py:35
+  OmniParser.forward                                     model/omniparser.py:19-32
+  token-id layout                                        utils/parser.py:16,88-105
+  checkpoint layout ``torch.load(path)['model']``        utils/checkpointer.py:20,44-47
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .nested_tensor import NestedTensor
+
+DEFAULT_CHARS = ' !"#$%&\'()*+,-./0123456789:;<=>?@ABCDEFGHIJKLMNOPQRSTUVWXYZ[\\]^_`abcdefghijklmnopqrstuvwxyz{|}~'
+
+
+@dataclass
+class OmniVocab:
+    """Same derivation as DefaultParser.parse_args (utils/parser.py:88-105)."""
+    chars: str = DEFAULT_CHARS
+    num_bins: int = 1000
+    rec_length: int = 25
+    pt_seq_length: int = 1024
+    vie_categories: int = 0
+    use_char_window_prompt: bool = True
+
+    def __post_init__(self):
+        n_char = len(self.chars) + 1
+        self.recog_pad_index = self.num_bins + n_char
+        self.pt_eos_index = self.recog_pad_index + 1
+        self.poly_eos_index = self.pt_eos_index + 1
+        self.rec_eos_index = self.poly_eos_index + 1
+        self.pt_sos_index = self.rec_eos_index + 1
+        self.poly_sos_index = self.pt_sos_index + 1
+        self.rec_sos_index = self.poly_sos_index + 1
+        self.padding_index = self.rec_sos_index + 1
+        self.num_classes = self.padding_index + 1 + self.vie_categories
+
+    def pt_prompt(self) -> torch.Tensor:
+        """engine/val.py:25-28"""
+        if self.use_char_window_prompt:
+            p = [0, 0, self.num_bins - 1, self.num_bins - 1, self.num_bins, self.num_bins + len(self.chars),
+                 self.pt_sos_index]
+        else:
+            p = [0, 0, self.num_bins - 1, self.num_bins - 1, self.pt_sos_index]
+        return torch.tensor([p], dtype=torch.long)
+
+
+class OmniParserB200:
+    """Inference-only stand-in for the reference ``OmniParser`` module (``--tfm_pre_norm --use_fpn``)."""
+
+    def __init__(self, state_dict, vocab: Optional[OmniVocab] = None, device: int = 0, stream: Optional[int] = None,
+                 ctx: Optional[_lib.Context] = None, workspace_mb: Optional[int] = None):
+        self.vocab = vocab or OmniVocab()
+        self.ctx = ctx or _lib.Context(device, stream)
+        if workspace_mb:
+            self.ctx.set_option('workspace_mb', workspace_mb)
+        kind = _lib.MODEL_OMNI_KIE if self.vocab.vie_categories else _lib.MODEL_OMNI_SPOT
+        self.ctx.load_state_dict(kind, state_dict)
+        self.lib = self.ctx.lib
+
+    # nn.Module look-alikes so reference drivers keep working
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    def __call__(self, samples, sequence=None):
+        return self.forward(samples, sequence)
+
+    # ---------------------------------------------------------------------------------------- stages
+    def encode(self, tensors: torch.Tensor, mask: Optional[torch.Tensor] = None):
+        """Swin-B -> FPN -> input_proj (model/omniparser.py:20-31).  Host or CUDA tensors."""
+        assert tensors.dim() == 4 and tensors.shape[1] == 3 and tensors.dtype == torch.float32
+        t = tensors.contiguous()
+        B, _, H, W = t.shape
+        mp = None
+        if mask is not None:
+            m8 = mask.to(torch.uint8).contiguous()
+            if bool(m8.any()):
+                self._keep_mask = m8
+                mp = m8.data_ptr()
+        self._keep_img = t
+        self.ctx.check(self.lib.alm_omni_encode(self.ctx.h, t.data_ptr(), mp, B, H, W))
+        return self.memory_shape()
+
+    def memory_shape(self):
+        b, h, w = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(self.lib.alm_omni_memory_shape(self.ctx.h, C.byref(b), C.byref(h), C.byref(w)))
+        return b.value, h.value, w.value
+
+    def features(self, level: int) -> torch.Tensor:
+        """LN'd Swin stage output, NCHW like ``features[level].tensors`` (backbone/joiner.py:10-18)."""
+        B, mh, mw = self.memory_shape()
+        H, W = self._keep_img.shape[2:]
+        hs, ws = (H + 3) // 4, (W + 3) // 4
+        for _ in range(level):
+            hs, ws = (hs + 1) // 2, (ws + 1) // 2
+        out = torch.empty(B, hs, ws, 128 << level, dtype=torch.float32)
+        self.ctx.check(self.lib.alm_omni_get_feature(self.ctx.h, level, out.data_ptr(), out.numel()))
+        return out.permute(0, 3, 1, 2)
+
+    def memory(self, which: int = 0) -> torch.Tensor:
+        """which 0: memory [B,M,512] (input_proj output, flattened); 1: sine position embedding."""
+        B, mh, mw = self.memory_shape()
+        out = torch.empty(B, mh * mw, 512, dtype=torch.float32)
+        self.ctx.check(self.lib.alm_omni_get_memory(self.ctx.h, which, out.data_ptr(), out.numel()))
+        return out
+
+    def _cfg(self, max_instances):
+        v = self.vocab
+        return _lib.DecodeCfg(v.num_bins, v.pt_eos_index, v.poly_eos_index, v.rec_eos_index, v.pt_sos_index,
+                              v.poly_sos_index, v.rec_sos_index, v.recog_pad_index, v.pt_seq_length, v.rec_length, 32,
+                              v.vie_categories, max_instances)
+
+    def decode(self, pt_prompt: Optional[torch.Tensor] = None):
+        """Greedy pt / poly / rec decoding of every encoded image (model/transformer.py:234-286).
+        Returns per-image reference-shaped outputs (None where no point was produced)."""
+        v = self.vocab
+        B, _, _ = self.memory_shape()
+        prompt = (pt_prompt if pt_prompt is not None else v.pt_prompt()).reshape(-1).to(torch.long).cpu().contiguous()
+        maxi = max(1, v.pt_seq_length // 2)
+        n_inst = np.zeros(B, dtype=np.int32)
+        pt = np.zeros((B, maxi, 2), dtype=np.int64)
+        poly = np.zeros((B, maxi, 32), dtype=np.int64)
+        rec = np.zeros((B, maxi, v.rec_length), dtype=np.int64)
+        prob = np.zeros((B, maxi, v.rec_length), dtype=np.float32)
+        cfg = self._cfg(maxi)
+        self.ctx.check(self.lib.alm_omni_decode(self.ctx.h, prompt.data_ptr(), prompt.numel(), C.byref(cfg),
+                                                n_inst.ctypes.data, pt.ctypes.data, poly.ctypes.data, rec.ctypes.data,
+                                                prob.ctypes.data))
+        outs = []
+        for b in range(B):
+            n = int(n_inst[b])
+            if n == 0:
+                outs.append(None)  # transformer.py:240-241
+                continue
+            outs.append(([torch.from_numpy(pt[b, :n].reshape(1, -1).copy()),
+                          torch.from_numpy(poly[b, :n].reshape(1, -1).copy()),
+                          torch.from_numpy(rec[b, :n][None].copy())],
+                         [torch.from_numpy(prob[b, :n].copy())]))
+        return outs
+
+    def decode_logits(self, image: int, kind: str, seq: torch.Tensor) -> torch.Tensor:
+        """Teacher-forced ``Transformer.decode`` (model/transformer.py:74-100): seq [n,len] -> [n,len,V]."""
+        k = {'pt': 0, 'poly': 1, 'rec': 2}[kind]
+        s = seq.to(torch.long).cpu().contiguous()
+        V = self.lib.alm_omni_vocab(self.ctx.h)
+        out = torch.empty(s.shape[0], s.shape[1], V, dtype=torch.float32)
+        self.ctx.check(self.lib.alm_omni_decode_logits(self.ctx.h, image, k, s.data_ptr(), s.shape[0], s.shape[1],
+                                                       out.data_ptr()))
+        return out
+
+    # ---------------------------------------------------------------------------------------- forward
+    def forward(self, samples: NestedTensor, sequence=None):
+        """Reference contract for batch 1 (engine/val.py:22,35): returns
+        ``([pt[1,2N], poly[1,32N], rec[1,N,L]], [probs[N,L]])`` or ``None``.
+        ``sequence`` = [pt_prompt, poly_prompt, rec_prompt, orig_size]; the poly/rec prompts are the fixed
+        sos tokens (val.py:30-31) and are validated, the pt prompt is passed through."""
+        outs = self.forward_batch(samples, sequence)
+        if len(outs) != 1:
+            raise ValueError('OmniParser.forward keeps the reference batch-1 contract; use forward_batch for B > 1')
+        return outs[0]
+
+    def forward_batch(self, samples: NestedTensor, sequence=None) -> List:
+        pt_prompt = None
+        if sequence is not None:
+            pt_prompt = sequence[0]
+            v = self.vocab
+            if int(sequence[1].reshape(-1)[0]) != v.poly_sos_index or int(sequence[2].reshape(-1)[0]) != v.rec_sos_index:
+                raise ValueError('poly/rec prompts must be the sos tokens of the vocabulary (engine/val.py:30-31)')
+        self.encode(samples.tensors, samples.mask)
+        return self.decode(pt_prompt)

@@ -1,0 +1,156 @@
+/*
+ * libalm_ocr.so -- C-ABI of the B200-native OCR forward path.
+ *
+ * The reference (AlibabaResearch/AdvancedLiterateMachinery) has no FFI table; its boundary for this
+ * path is two Python `nn.Module.forward` call sites plus two checkpoint layouts:
+ *
+ *   OmniParser : `output = model(samples, seqs)`      OCR/OmniParser/engine/val.py:35
+ *                (OmniParser.forward, OCR/OmniParser/model/omniparser.py:19-32)
+ *   MGP-STR    : `model(image, is_eval=True)`         OCR/MGP-STR/demo.py:33, test_final.py:140
+ *                (MGPSTR.forward, OCR/MGP-STR/modules/mgp_str.py:96-101)
+ *   weights    : torch.load(path)['model']            OCR/OmniParser/utils/checkpointer.py:20,44-47
+ *                bare state_dict 'module.mgp_str.*'   OCR/MGP-STR/test_final.py:348,356
+ *
+ * The only native-API precedent in the reference is the two-function iOS library
+ * `init_ocr(path, threads)` / `ocr_recognize(data, w, h, c, flag)`
+ * (OCR/LiteWeightOCR/.../Headers/LiteWeight_Mobile_OCR_Recognize.h:17-19); this header keeps that
+ * shape: init -> load -> run -> free, plain pointers and sizes, no C++ or torch types.
+ *
+ * Conventions: every function returns 0 or a negative ALM_ERR_* code and never throws across the
+ * ABI; `alm_last_error` gives the message.  One `alm_ctx` per GPU per thread (no internal locking).
+ * All kernels are enqueued on the context's stream.  Inputs are caller-owned (host or device
+ * pointers are both accepted: host buffers are staged through pinned memory inside the call);
+ * outputs are written to caller-provided host buffers after a stream synchronise.
+ */
+#ifndef ALM_OCR_H_
+#define ALM_OCR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ALM_API __attribute__((visibility("default")))
+#else
+#define ALM_API
+#endif
+
+#define ALM_OK 0
+#define ALM_ERR_INVALID (-1)   /* bad argument / missing tensor / shape mismatch          */
+#define ALM_ERR_CUDA (-2)      /* CUDA runtime or driver error (message has the call)      */
+#define ALM_ERR_OOM (-3)       /* workspace arena or weight slab exhausted                 */
+#define ALM_ERR_STATE (-4)     /* call order violated (e.g. decode before encode)          */
+#define ALM_ERR_UNSUPPORTED (-5)
+
+typedef struct alm_ctx alm_ctx;
+
+/* model kinds for alm_load_weights */
+#define ALM_MODEL_OMNI_SPOT 1 /* OmniParser text spotting (V = 1104)                         */
+#define ALM_MODEL_OMNI_KIE 2  /* OmniParser KIE: V = 1104 + vie_categories (derived from V) */
+#define ALM_MODEL_MGPSTR 3    /* MGP-STR (dim/depth/heads derived from the tensors)          */
+
+/* element types of alm_tensor_desc.data */
+#define ALM_F32 0
+#define ALM_F16 1
+#define ALM_BF16 2
+#define ALM_I64 3
+
+/* One state-dict entry.  `name` is the reference key verbatim
+ * (e.g. "backbone.0.layers.2.blocks.5.attn.qkv.weight", "module.mgp_str.blocks.0.norm1.bias").
+ * `data` is a HOST pointer; the library converts and uploads, the caller keeps ownership. */
+typedef struct alm_tensor_desc {
+  const char* name;
+  const void* data;
+  int dtype;
+  int ndim;
+  int64_t shape[4];
+} alm_tensor_desc;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on, or NULL for a private stream. */
+ALM_API int alm_init(int device, void* stream, alm_ctx** out);
+ALM_API void alm_free(alm_ctx* ctx);
+ALM_API const char* alm_last_error(const alm_ctx* ctx); /* valid until the next call on ctx */
+ALM_API const char* alm_version(void);
+
+/* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
+ *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb". */
+ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
+/* kernels launched on this context since the last call with reset != 0 */
+ALM_API long alm_launch_count(alm_ctx* ctx, int reset);
+
+/* Replaces reference `model.load_state_dict(torch.load(path)['model'])`
+ * (OCR/OmniParser/utils/checkpointer.py:44-47; OCR/MGP-STR/test_final.py:353-356). */
+ALM_API int alm_load_weights(alm_ctx* ctx, int model_kind, const alm_tensor_desc* tensors, int n);
+
+/* ---- OmniParser ---------------------------------------------------------------------------- */
+/* Vocabulary / decode configuration: OCR/OmniParser/utils/parser.py:16-21,91-103. */
+typedef struct alm_decode_cfg {
+  int num_bins;       /* 1000 */
+  int pt_eos, poly_eos, rec_eos, pt_sos, poly_sos, rec_sos, recog_pad;
+  int pt_seq_length;  /* --pt_seq_length : max generated pt tokens                           */
+  int rec_length;     /* --rec_length    : 25                                                */
+  int poly_length;    /* 32 (transformer.py:254)                                             */
+  int vie_categories; /* 0 for text spotting                                                 */
+  int max_instances;  /* capacity of the per-image output buffers (>= pt_seq_length / 2)      */
+} alm_decode_cfg;
+
+/* Replaces `features, pos = self.backbone(samples)`, FPN and input_proj
+ * (OCR/OmniParser/model/omniparser.py:20-31): Swin-B encoder -> FPN -> 1x1 stride-2 projection.
+ * img  : f32 [B,3,H,W] normalised pixels (NestedTensor.tensors), host or device.
+ * mask : u8  [B,H,W], 1 = padding (NestedTensor.mask), host or device, or NULL for all-valid.
+ * The image memory ([B, M, 512], M = ceil(H/16)*ceil(W/16)) stays resident in the context. */
+ALM_API int alm_omni_encode(alm_ctx* ctx, const float* img, const uint8_t* mask, int B, int H, int W);
+
+/* Staged-parity readbacks (host buffers).
+ * level 0..3 : LN'd Swin stage outputs, NHWC f32 [B, S_l, S_l', 128<<l]  (joiner.py:10-18)
+ * which 0 = memory [B,M,512], 1 = sine position embedding [B,M,512]       (position_embedding.py:24-44) */
+ALM_API int alm_omni_get_feature(alm_ctx* ctx, int level, float* out, size_t out_elems);
+ALM_API int alm_omni_get_memory(alm_ctx* ctx, int which, float* out, size_t out_elems);
+ALM_API int alm_omni_memory_shape(alm_ctx* ctx, int* B, int* h, int* w);
+
+/* Replaces `self.transformer(self.input_proj(src), mask, pos, sequence)` in eval mode
+ * (OCR/OmniParser/model/transformer.py:234-286): greedy point / polygon / recognition decoding for
+ * every encoded image, each image keeping the reference's batch-1 semantics.
+ * pt_prompt: int64 [n_prompt] (engine/val.py:25-28).  Outputs (host), per image b:
+ *   n_inst[b]                         number of decoded points (0 <=> the reference returns None)
+ *   pt  [b, max_inst, 2]   int64      transformer.py:134-141
+ *   poly[b, max_inst, 32]  int64      transformer.py:265
+ *   rec [b, max_inst, rec_length]     transformer.py:284
+ *   rec_prob [b, max_inst, rec_length] f32   transformer.py:286 */
+ALM_API int alm_omni_decode(alm_ctx* ctx, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_inst,
+                    int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);
+
+/* Teacher-forced logits: replaces `Transformer.decode(input_seq, memory, mask, pos_embed, input_type)`
+ * (transformer.py:74-100) for image `image`: seq int64 [n_seq, len] -> logits f32 [n_seq, len, V].
+ * kind: 0 = pt, 1 = poly, 2 = rec. */
+ALM_API int alm_omni_decode_logits(alm_ctx* ctx, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits);
+ALM_API int alm_omni_vocab(alm_ctx* ctx);
+
+/* ---- MGP-STR ------------------------------------------------------------------------------- */
+/* Replaces `model(image, is_eval=True)` (OCR/MGP-STR/modules/mgp_str.py:96-101).
+ * img: f32 [B,3,32,128] in [0,1].  Any output pointer may be NULL.  Host buffers:
+ *   attn   [3][B,27,257] f32 (char, bpe, wp A^3 maps)
+ *   char_logits [B,27,38], bpe_logits [B,27,50257], wp_logits [B,27,30522]  f32
+ *   ids    [3][B,27] int32 top-1 ids, prob [3][B,27] f32 max softmax prob (demo.py:36-60). */
+ALM_API int alm_mgpstr_forward(alm_ctx* ctx, const float* img, int B, float* attn, float* char_logits, float* bpe_logits,
+                       float* wp_logits, int32_t* ids, float* prob);
+
+/* ---- low-level ops (unit parity tests call these through the ABI; device pointers only) ------ */
+/* C[M,N] f32 = A[M,K] f32 * W[N,K]^T f32 (+bias[N]) with act 0 none / 1 gelu(erf) / 2 relu; runs the same
+ * operand split + tcgen05 kernel as the model graphs.  batch > 1: contiguous batches of A, W and C. */
+ALM_API int alm_op_linear(alm_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                  int act, int batch);
+ALM_API int alm_op_layernorm(alm_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps, float* y,
+                     long rows, int C);
+/* Swin W-MSA core on an already windowed qkv tensor [B*nWh*nWw*49, 3C] (swin_transformer.py:127-148). */
+ALM_API int alm_op_window_attention(alm_ctx* ctx, const float* qkv, const float* bias_table /*[169,heads]*/, float* out,
+                            int B, int nWh, int nWw, int C, int heads, int shift);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALM_OCR_H_ */
