@@ -44,6 +44,8 @@ SIGNATURES = {
     'alm_version': (C.c_char_p, []),
     'alm_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
+    'alm_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+    'alm_bench_gemm': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     'alm_load_weights': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorDesc), C.c_int]),
     'alm_omni_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'alm_omni_get_feature': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
@@ -99,6 +101,16 @@ class Context:
 
     def set_option(self, key: str, value: int):
         self.check(self.lib.alm_set_option(self.h, key.encode(), int(value)))
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_long()
+        self.check(self.lib.alm_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
+    def bench_gemm(self, M, N, K, iters=20) -> float:
+        ms = C.c_float()
+        self.check(self.lib.alm_bench_gemm(self.h, M, N, K, iters, C.byref(ms)))
+        return ms.value
 
     def launch_count(self, reset=False) -> int:
         return int(self.lib.alm_launch_count(self.h, 1 if reset else 0))

@@ -133,6 +133,10 @@ struct Ctx {
   int nsplit = 3;     // 3 = bf16x3 split (fp32-class), 1 = single-pass bf16
   PFN_encodeTiled encode = nullptr;
   long launches = 0;  // kernels launched since last reset (gpu_launches in bench.py)
+  // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
+  int profile_gemm = 0;
+  struct GemmRec { cudaEvent_t a, b; double flops; };
+  std::vector<GemmRec> gemm_recs;
   OmniModel* omni = nullptr;
   MgpModel* mgp = nullptr;
   std::vector<void*> weight_slabs;

@@ -158,6 +158,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "gemm_impl") {
       ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "gemm_impl must be 0 or 1");
       h->c.gemm_impl = static_cast<int>(value);
+    } else if (k == "profile_gemm") {
+      h->c.profile_gemm = value ? 1 : 0;
     } else if (k == "workspace_mb") {
       ALM_REQUIRE(value >= 64 && h->c.ws.base == nullptr, ALM_ERR_STATE, "workspace_mb must be set before first use");
       h->c.ws_bytes = static_cast<size_t>(value) << 20;
@@ -172,6 +174,64 @@ long alm_launch_count(alm_ctx* h, int reset) {
   const long n = h->c.launches;
   if (reset) h->c.launches = 0;
   return n;
+}
+
+int alm_profile_read(alm_ctx* h, double* gemm_ms, double* gemm_flops, long* gemm_launches) {
+  return guarded(h, [&] {
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+    double ms = 0, fl = 0;
+    for (auto& r : h->c.gemm_recs) {
+      float t = 0;
+      ALM_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      ms += t;
+      fl += r.flops;
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = fl;
+    if (gemm_launches) *gemm_launches = static_cast<long>(h->c.gemm_recs.size());
+    h->c.gemm_recs.clear();
+  });
+}
+
+int alm_bench_gemm(alm_ctx* h, int M, int N, int K, int iters, float* ms_per_launch) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0 && iters > 0 && ms_per_launch, ALM_ERR_INVALID,
+                "alm_bench_gemm arguments");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    float* fa = c->ws.get<float>(static_cast<size_t>(M) * K);
+    float* fb = c->ws.get<float>(static_cast<size_t>(N) * K);
+    // any finite data does; reuse whatever the arena holds after clamping it through a split
+    ALM_CHECK_CUDA(cudaMemsetAsync(fa, 0x3c, static_cast<size_t>(M) * K * 4, c->stream));
+    ALM_CHECK_CUDA(cudaMemsetAsync(fb, 0x3c, static_cast<size_t>(N) * K * 4, c->stream));
+    Operand a, b;
+    bf16* ah = c->ws.get<bf16>(static_cast<size_t>(M) * K); bf16* al = c->ws.get<bf16>(static_cast<size_t>(M) * K);
+    bf16* bh = c->ws.get<bf16>(static_cast<size_t>(N) * K); bf16* bl = c->ws.get<bf16>(static_cast<size_t>(N) * K);
+    split_rows(c, fa, K, M, K, ah, al, K);
+    split_rows(c, fb, K, N, K, bh, bl, K);
+    a.hi = ah; a.lo = al; a.rows = M; a.K = K; a.ld = K;
+    b.hi = bh; b.lo = bl; b.rows = N; b.K = K; b.ld = K;
+    Epilogue e;
+    e.out_f32 = c->ws.get<float>(static_cast<size_t>(M) * N);
+    e.ldo = N;
+    for (int i = 0; i < 3; ++i) gemm(c, a, b, e);
+    cudaEvent_t e0, e1;
+    ALM_CHECK_CUDA(cudaEventCreate(&e0));
+    ALM_CHECK_CUDA(cudaEventCreate(&e1));
+    ALM_CHECK_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; ++i) gemm(c, a, b, e);
+    ALM_CHECK_CUDA(cudaEventRecord(e1, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    ALM_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / iters;
+    c->ws.release(mk);
+  });
 }
 
 int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors, int n) {

@@ -424,6 +424,12 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
   const int nsplit = c->nsplit;
   ALM_REQUIRE(nsplit == 1 || (A.lo && B.lo), ALM_ERR_INVALID, "gemm: split mode needs lo operands");
 
+  Ctx::GemmRec rec{nullptr, nullptr, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1};
+  if (c->profile_gemm) {
+    ALM_CHECK_CUDA(cudaEventCreate(&rec.a));
+    ALM_CHECK_CUDA(cudaEventCreate(&rec.b));
+    ALM_CHECK_CUDA(cudaEventRecord(rec.a, c->stream));
+  }
   if (c->gemm_impl == 1) {
     p.n_blocks = 0; p.num_tiles = 0;
     SimtOperand sa{A.hi, A.lo, A.ld, A.bs0, A.bs1}, sb{B.hi, B.lo, B.ld, B.bs0, B.bs1};
@@ -432,6 +438,10 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
   } else {
     if (nsplit == 3) launch_tc<128, 3>(c, A, B, p);
     else launch_tc<128, 1>(c, A, B, p);
+  }
+  if (c->profile_gemm) {
+    ALM_CHECK_CUDA(cudaEventRecord(rec.b, c->stream));
+    c->gemm_recs.push_back(rec);
   }
   count_launch(c);
   check_launch("gemm");

@@ -77,10 +77,18 @@ ALM_API const char* alm_last_error(const alm_ctx* ctx); /* valid until the next 
 ALM_API const char* alm_version(void);
 
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
- *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb". */
+ *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm". */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
 /* kernels launched on this context since the last call with reset != 0 */
 ALM_API long alm_launch_count(alm_ctx* ctx, int reset);
+
+/* Per-GEMM device timing (measurement aid, off by default): after alm_set_option(ctx, "profile_gemm", 1) every
+ * tensor-core GEMM launch is bracketed by CUDA events on the context stream.  alm_profile_read synchronises,
+ * returns the summed kernel time (ms), the summed algorithmic FLOPs (2*M*N*K) and the launch count, and clears. */
+ALM_API int alm_profile_read(alm_ctx* ctx, double* gemm_ms, double* gemm_flops, long* gemm_launches);
+/* Times `iters` back-to-back launches of one [M,K]x[N,K]^T GEMM (operands pre-split, resident) with CUDA events
+ * on the context stream; ms_per_launch is the average kernel duration. */
+ALM_API int alm_bench_gemm(alm_ctx* ctx, int M, int N, int K, int iters, float* ms_per_launch);
 
 /* Replaces reference `model.load_state_dict(torch.load(path)['model'])`
  * (OCR/OmniParser/utils/checkpointer.py:44-47; OCR/MGP-STR/test_final.py:353-356). */

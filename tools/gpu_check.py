@@ -226,7 +226,35 @@ def g_perf():
         del m
 
 
-GROUPS = {'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
+def g_mgp():
+    import numpy as np
+    import torch
+    from advancedliteratemachinery_b200 import MGPSTRB200
+    from advancedliteratemachinery_b200 import synthetic as W
+    from oracle import mgpstr_ref as M
+    torch.set_grad_enabled(False)
+    sd = W.mgpstr_state_dict(seed=0)
+    m = MGPSTRB200(sd)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(3, 3, 32, 128, generator=g)
+    ref = M.forward(img, sd)
+    out = m(img, is_eval=True)
+    for i, nm in enumerate(('char', 'bpe', 'wp')):
+        print(f'mgp attn[{nm}]: {_err(out[0][i], ref[0][i])}')
+        print(f'mgp logits[{nm}]: {_err(out[1 + i], ref[1 + i])}  ids match={torch.equal(m.last_ids[i].long(), ref[1 + i].argmax(-1))}')
+    for B in (64, 512):
+        img = torch.rand(B, 3, 32, 128, device='cuda')
+        for ns in (3, 1):
+            m.ctx.set_option('nsplit', ns)
+            for it in range(3):
+                torch.cuda.synchronize(); t = time.time()
+                m.forward(img, is_eval=True, want_logits=False)
+                dt = time.time() - t
+            print(f'mgp B={B} nsplit={ns}: {dt * 1e3:.1f} ms -> {B / dt:.0f} crops/s ({49.75e9 * B / dt / 1e12:.1f} algorithmic TFLOP/s)', flush=True)
+        m.ctx.set_option('nsplit', 3)
+
+
+GROUPS = {'mgp': g_mgp, 'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
           'enc': g_enc, 'dec': g_dec, 'perf': g_perf}
 
 if __name__ == '__main__':
