@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -133,6 +134,26 @@ struct Ctx {
   int nsplit = 3;     // 3 = bf16x3 split (fp32-class), 1 = single-pass bf16
   PFN_encodeTiled encode = nullptr;
   long launches = 0;  // kernels launched since last reset (gpu_launches in bench.py)
+  // memoised TMA descriptors (see gemm.cu)
+  struct TmapKey {
+    const void* base; int K, rows; long ld; int nb0, nb1; long bs0, bs1; int box_rows;
+    bool operator==(const TmapKey& o) const {
+      return base == o.base && K == o.K && rows == o.rows && ld == o.ld && nb0 == o.nb0 && nb1 == o.nb1 &&
+             bs0 == o.bs0 && bs1 == o.bs1 && box_rows == o.box_rows;
+    }
+  };
+  struct TmapHash {
+    size_t operator()(const TmapKey& k) const {
+      size_t h = reinterpret_cast<size_t>(k.base);
+      auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+      mix(k.K); mix(k.rows); mix(static_cast<size_t>(k.ld)); mix(k.nb0); mix(k.nb1);
+      mix(static_cast<size_t>(k.bs0)); mix(static_cast<size_t>(k.bs1)); mix(k.box_rows);
+      return h;
+    }
+  };
+  std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
+  int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps
+  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
   struct GemmRec { cudaEvent_t a, b; double flops; };

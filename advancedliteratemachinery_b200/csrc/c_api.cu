@@ -158,6 +158,10 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "gemm_impl") {
       ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "gemm_impl must be 0 or 1");
       h->c.gemm_impl = static_cast<int>(value);
+    } else if (k == "wattn_impl") {
+      h->c.wattn_impl = value ? 1 : 0;
+    } else if (k == "use_graphs") {
+      h->c.use_graphs = value ? 1 : 0;
     } else if (k == "profile_gemm") {
       h->c.profile_gemm = value ? 1 : 0;
     } else if (k == "workspace_mb") {

@@ -4,7 +4,8 @@
 //
 //     warp 0          : TMA producer       (one elected lane)
 //     warp 1          : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//     warps 2..5      : epilogue           (TMEM -> registers -> fused bias/act/residual/scatter -> global)
+//     warps 2..9      : epilogue           (TMEM -> registers -> smem transpose -> fused bias/act/residual/
+//                                           scatter -> fully coalesced global stores)
 //
 // Precision: the reference computes in fp32.  bf16 tensor-core operands alone would miss the
 // "logits within 1e-3" bar, so every fp32 matrix is carried as a (hi, lo) bf16 pair with hi + lo == x to
@@ -25,8 +26,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
-constexpr int kEpiWarp0 = 2;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -46,9 +47,11 @@ struct SmemLayout {
   static constexpr int kNumA = (NSPLIT == 3) ? 2 : 1;
   static constexpr int kNumB = (NSPLIT == 3) ? 2 : 1;
   static constexpr int kStageBytes = kNumA * kABytes + kNumB * kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // one XOR-swizzled 32x32 fp32 block per epilogue warp
+  static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;  // +1024 alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -71,6 +74,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
+  static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -85,7 +89,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty[s], kEpiWarps);  // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -166,9 +170,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
     }
   } else {
-    // ===================================================================== epilogue warps
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================================================================== epilogue warps (8)
+    // warp -> (TMEM lane quarter, column half).  Each 32x32 accumulator block is read row-per-thread from TMEM,
+    // transposed through an XOR-swizzled 4 KB staging block in shared memory, and then handled four columns per
+    // thread / eight threads per row, so that every global access (bias, residual, outputs) is a full 128 B line.
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
+    const int half = (warp - 2) >> 2;      // 32-column chunks c = half, half + 2, ... of the tile
+    float* stg = reinterpret_cast<float*>(smem + L::kStages * L::kStageBytes + L::kBarBytes) + (warp - 2) * 1024;
     const Epilogue& e = p.e;
+    const int rl_base = lane >> 3, j4 = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
     for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -178,97 +188,86 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int b0 = batch % p.nb0, b1 = batch / p.nb0;
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
-
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      long orow = row;
-      if (row_ok && e.out_map) orow = e.out_map[row];
-      const bool store_ok = row_ok && orow >= 0;
-      long rrow = orow;
-      if (store_ok && e.resid_map) rrow = e.resid_map[row];
-      const long obase = static_cast<long>(b0) * e.obs0 + static_cast<long>(b1) * e.obs1 + orow * e.ldo;
-      const float* rptr =
-          e.resid ? e.resid + static_cast<long>(b0) * e.rbs0 + static_cast<long>(b1) * e.rbs1 + rrow * e.ldr : nullptr;
+      const long obatch = static_cast<long>(b0) * e.obs0 + static_cast<long>(b1) * e.obs1;
+      const float* rbatch = e.resid ? e.resid + static_cast<long>(b0) * e.rbs0 + static_cast<long>(b1) * e.rbs1 : nullptr;
       const float* bias = e.bias ? e.bias + static_cast<long>(b0) * e.bias_bs0 : nullptr;
-      const float row_bias = (bias && e.bias_mode == BIAS_ROW && row_ok) ? bias[row] : 0.0f;
+      const int row_base = m_blk * BLOCK_M + quarter * 32;
+      const bool rows_live = row_base < p.M;
 
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + c * 32, v);
         ptx::tmem_ld_wait();
         const int col0 = n_blk * BLOCK_N + c * 32;
-        if (!store_ok || col0 >= p.N) continue;
-        float f[32];
+        if (!rows_live || col0 >= p.N) continue;  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * e.alpha + row_bias;
-        const bool full = (col0 + 32 <= p.N) && p.vec_ok;
-        if (full) {
-          if (bias && e.bias_mode == BIAS_COL) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + col0 + j);
-              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = col0 + j4 * 4;
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rl_base;
+          const int row = row_base + rl;
+          const float4 acc = *reinterpret_cast<const float4*>(stg + rl * 32 + ((j4 ^ (rl & 7)) << 2));
+          if (row >= p.M || col >= p.N) continue;
+          long orow = row;
+          if (e.out_map) orow = e.out_map[row];
+          if (orow < 0) continue;
+          long rrow = orow;
+          if (e.resid_map) rrow = e.resid_map[row];
+          const long o = obatch + orow * e.ldo + col;
+          float f[4] = {acc.x * e.alpha, acc.y * e.alpha, acc.z * e.alpha, acc.w * e.alpha};
+          if (bias && e.bias_mode == BIAS_ROW) {
+            const float rb = bias[row];
+            f[0] += rb; f[1] += rb; f[2] += rb; f[3] += rb;
+          }
+          if (p.vec_ok && col + 3 < p.N) {
+            if (bias && e.bias_mode == BIAS_COL) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + col);
+              f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
             }
-          }
-          if (e.act == ACT_GELU) {
+            if (e.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          } else if (e.act == ACT_RELU) {
+              for (int q = 0; q < 4; ++q) f[q] = gelu_erf(f[q]);
+            } else if (e.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (rptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 rr = *reinterpret_cast<const float4*>(rptr + col0 + j);
-              f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
+              for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.0f);
             }
-          }
-          if (e.out_f32) {
-            float4* o = reinterpret_cast<float4*>(e.out_f32 + obase + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-          if (e.out_hi) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              bf16 h0, l0, h1, l1;
-              split_bf16(f[2 * j], h0, l0);
-              split_bf16(f[2 * j + 1], h1, l1);
-              hi[j] = pack_bf16(h0, h1);
-              lo[j] = pack_bf16(l0, l1);
+            if (rbatch) {
+              const float4 rr = *reinterpret_cast<const float4*>(rbatch + rrow * e.ldr + col);
+              f[0] += rr.x; f[1] += rr.y; f[2] += rr.z; f[3] += rr.w;
             }
-            uint4* oh = reinterpret_cast<uint4*>(e.out_hi + obase + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (e.out_lo) {
-              uint4* ol = reinterpret_cast<uint4*>(e.out_lo + obase + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-        } else {
-          // ragged / unaligned tail: scalar, guarded
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col >= p.N) break;
-            float x = f[j];
-            if (bias && e.bias_mode == BIAS_COL) x += bias[col];
-            if (e.act == ACT_GELU) x = gelu_erf(x);
-            else if (e.act == ACT_RELU) x = fmaxf(x, 0.0f);
-            if (rptr) x += rptr[col];
-            if (e.out_f32) e.out_f32[obase + col] = x;
+            if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(f[0], f[1], f[2], f[3]);
             if (e.out_hi) {
-              bf16 h, l;
-              split_bf16(x, h, l);
-              e.out_hi[obase + col] = h;
-              if (e.out_lo) e.out_lo[obase + col] = l;
+              bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+              split_bf16(f[0], h0, l0); split_bf16(f[1], h1, l1); split_bf16(f[2], h2, l2); split_bf16(f[3], h3, l3);
+              *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+              if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+            }
+          } else {
+            // ragged / unaligned tail: scalar, guarded
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col + q >= p.N) break;
+              float x = f[q];
+              if (bias && e.bias_mode == BIAS_COL) x += bias[col + q];
+              if (e.act == ACT_GELU) x = gelu_erf(x);
+              else if (e.act == ACT_RELU) x = fmaxf(x, 0.0f);
+              if (rbatch) x += rbatch[rrow * e.ldr + col + q];
+              if (e.out_f32) e.out_f32[o + q] = x;
+              if (e.out_hi) {
+                bf16 h, l;
+                split_bf16(x, h, l);
+                e.out_hi[o + q] = h;
+                if (e.out_lo) e.out_lo[o + q] = l;
+              }
             }
           }
         }
+        __syncwarp();  // staging block is reused by the next chunk
       }
       // release the accumulator stage back to the MMA warp
       ptx::tc_fence_before();
@@ -348,7 +347,13 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
   }
 }
 
-CUtensorMap make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows) {
+// Encoding a descriptor is a driver call (a few microseconds); the decode loop re-issues the same few hundred
+// (pointer, geometry) pairs every token, so descriptors are memoised per context.
+const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows) {
+  Ctx::TmapKey key{base, op.K, op.rows, op.ld, op.nb0, op.nb1, op.bs0, op.bs1, box_rows};
+  auto it = c->tmap_cache.find(key);
+  if (it != c->tmap_cache.end()) return it->second;
+  if (c->tmap_cache.size() > 20000) c->tmap_cache.clear();
   CUtensorMap tm;
   ALM_REQUIRE(base != nullptr, ALM_ERR_INVALID, "gemm operand pointer is null");
   ALM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, ALM_ERR_INVALID, "gemm operand not 16-byte aligned");
@@ -370,7 +375,7 @@ CUtensorMap make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows)
     throw AlmError{ALM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)) +
                                      " (K=" + std::to_string(op.K) + " rows=" + std::to_string(op.rows) +
                                      " ld=" + std::to_string(op.ld) + ")"};
-  return tm;
+  return c->tmap_cache.emplace(key, tm).first->second;
 }
 
 template <int BLOCK_N, int NSPLIT>
@@ -384,13 +389,10 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   }
   p.n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_tiles = static_cast<long>(p.m_blocks) * p.n_blocks * p.nb0 * p.nb1;
-  CUtensorMap ta_hi = make_tmap(c, A.hi, A, BLOCK_M);
-  CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N);
-  CUtensorMap ta_lo = ta_hi, tb_lo = tb_hi;
-  if (NSPLIT == 3) {
-    ta_lo = make_tmap(c, A.lo, A, BLOCK_M);
-    tb_lo = make_tmap(c, B.lo, B, BLOCK_N);
-  }
+  const CUtensorMap ta_hi = make_tmap(c, A.hi, A, BLOCK_M);  // by value: the cache may be cleared by a later call
+  const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N);
+  const CUtensorMap ta_lo = (NSPLIT == 3) ? make_tmap(c, A.lo, A, BLOCK_M) : ta_hi;
+  const CUtensorMap tb_lo = (NSPLIT == 3) ? make_tmap(c, B.lo, B, BLOCK_N) : tb_hi;
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, c->num_sms));
   kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
@@ -436,8 +438,17 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
     dim3 grid((p.N + 15) / 16, (p.M + 15) / 16, p.nb0 * p.nb1);
     gemm_simt_kernel<<<grid, dim3(16, 16), 0, c->stream>>>(sa, sb, p, nsplit);
   } else {
-    if (nsplit == 3) launch_tc<128, 3>(c, A, B, p);
-    else launch_tc<128, 1>(c, A, B, p);
+    // Few-tile problems (the per-token decoder GEMMs: M <= a few hundred rows) are bound by what ONE SM can pull
+    // through its TMA port, so they run with 32-wide column tiles to spread the weight stream over 4x more SMs.
+    const long tiles128 = static_cast<long>(p.m_blocks) * ((p.N + 127) / 128) * p.nb0 * p.nb1;
+    const bool narrow = tiles128 < c->num_sms / 2 && p.N > 32;
+    if (nsplit == 3) {
+      if (narrow) launch_tc<32, 3>(c, A, B, p);
+      else launch_tc<128, 3>(c, A, B, p);
+    } else {
+      if (narrow) launch_tc<32, 1>(c, A, B, p);
+      else launch_tc<128, 1>(c, A, B, p);
+    }
   }
   if (c->profile_gemm) {
     ALM_CHECK_CUDA(cudaEventRecord(rec.b, c->stream));

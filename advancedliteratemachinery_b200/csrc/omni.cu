@@ -320,7 +320,10 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   SplitBuf cat = alloc_split(c, BM * 1024);
   fpn_assemble(c, p[0], p[1], p[2], p[3], B, m->Hs, m->Ws, m->mh, m->mw, cat.hi, cat.lo);
   linear(c, cat, BM, m->inproj, ACT_NONE, m->memory, nullptr);
-  sine_pos(c, mask, B, H, W, m->mh, m->mw, m->dim_t, m->pos, m->kpm);
+  {
+    float* scratch = ws.get<float>(static_cast<size_t>(2) * BM);
+    sine_pos(c, mask, B, H, W, m->mh, m->mw, m->dim_t, m->pos, m->kpm, scratch);
+  }
   // operands for the cross-attention K/V projections: memory and memory + pos
   SplitBuf mem = alloc_split(c, BM * 512), memp = alloc_split(c, BM * 512);
   gather_ln(c, m->memory, 512, nullptr, 1, 512, BM, nullptr, nullptr, 0.f, false, m->pos, 512, nullptr, 0, mem.hi,
@@ -349,6 +352,8 @@ namespace {
 struct DecodeBufs {
   int S = 0, Tmax = 0, Ncap = 0;
   float* x = nullptr;
+  float* qpos = nullptr;  // [512] query_pos of the current step
+  int* tpos = nullptr;    // device-side position counter (so one captured graph serves every token)
   SplitBuf ln, lnp, att, q, o, hid, h0, h1;
   float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr;
   SplitBuf prob;
@@ -361,6 +366,8 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
   d.S = B * Ncap; d.Tmax = Tmax; d.Ncap = Ncap;
   const size_t S = d.S;
   d.x = c->ws.get<float>(S * 512);
+  d.qpos = c->ws.get<float>(512);
+  d.tpos = c->ws.get<int>(1);
   d.ln = alloc_split(c, S * 512);
   d.lnp = alloc_split(c, S * 512);
   d.att = alloc_split(c, S * 512);
@@ -381,14 +388,14 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
   return d;
 }
 
-// One decoder pass over the token at position t of every sequence (pre-norm layer, transformer.py:430-454,
+// One decoder pass over the token at position *u.tpos of every sequence (pre-norm layer, transformer.py:430-454,
 // with self-attention K/V cached and the cross-attention K/V precomputed per image).
 // img0: first image of the batch slice the S sequences belong to; nimg images x Ncap sequences each.
-void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, int tstride, int t, int img0, int nimg,
+void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, int tstride, int img0, int nimg,
                   bool want_logits) {
   const int S = u.S, Ncap = u.Ncap, M = m->M, Mpad = m->Mpad;
-  const float* qpos = m->pos_emb[d] + static_cast<long>(t) * 512;
-  embed_ln(c, tokens, tstride, t, S, m->word_emb, m->pos_emb[d], m->emb_norm.g, m->emb_norm.b, u.x);
+  embed_ln(c, tokens, tstride, u.tpos, S, m->word_emb, m->pos_emb[d], m->emb_norm.g, m->emb_norm.b, u.x, u.qpos);
+  const float* qpos = u.qpos;
   for (int l = 0; l < 4; ++l) {
     const DecLayerW& w = m->dec[d][l];
     const long dl = static_cast<long>(d) * 4 + l;
@@ -397,7 +404,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
               u.lnp.hi, u.lnp.lo);
     linear(c, u.lnp, S, w.sa_qk, ACT_NONE, u.qk, nullptr);
     linear(c, u.ln, S, w.sa_v, ACT_NONE, u.v, nullptr);
-    self_attn_step(c, u.qk, u.v, u.kc[l], u.vc[l], S, t, u.Tmax, u.att.hi, u.att.lo);
+    self_attn_step(c, u.qk, u.v, u.kc[l], u.vc[l], S, u.tpos, u.Tmax, u.att.hi, u.att.lo);
     linear(c, u.att, S, w.sa_out, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
     // --- cross attention against the per-image cached K / V^T
     gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n2.g, w.n2.b, 1e-5f, false, qpos, 0, nullptr, 0, nullptr, nullptr, 512,
@@ -441,6 +448,68 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
   linear(c, u.h1, S, m->head[d][2], ACT_NONE, u.logits, nullptr);
 }
 
+struct HeadArgs {
+  bool on = false;
+  HeadCfg cfg{};
+  int* tokens = nullptr;
+  int tstride = 0, n_prompt_m1 = 0;
+  float* probs = nullptr;
+  int pstride = 0;
+  int* finished = nullptr;
+  int* ntok = nullptr;
+  int seqs_per_image = 1;
+};
+
+// `n` consecutive token steps of decoder d.  The step (all ~62 launches + the counter increment) is captured once
+// into a CUDA graph per distinct (shape, pointer) signature and replayed: the per-token host cost drops from
+// ~62 launches to one cudaGraphLaunch.
+void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, int tstride, int img0, int nimg, int n,
+               const HeadArgs& h) {
+  if (n <= 0) return;
+  auto body = [&] {
+    decoder_step(c, m, d, u, tokens, tstride, img0, nimg, h.on);
+    if (h.on)
+      head_select(c, u.logits, u.S, m->V, m->V, d, h.cfg, h.tokens, h.tstride, u.tpos, h.n_prompt_m1, h.probs, h.pstride,
+                  h.finished, h.ntok, h.seqs_per_image);
+    add_i32(c, u.tpos, 1);
+  };
+  if (!c->use_graphs || c->profile_gemm || c->gemm_impl != 0) {
+    for (int i = 0; i < n; ++i) body();
+    return;
+  }
+  std::vector<long> key = {d, u.S, u.Ncap, u.Tmax, img0, nimg, m->M, h.on ? 1 : 0, c->nsplit,
+                           reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
+                           reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
+                           reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
+                           h.cfg.rec_eos, h.cfg.recog_pad};
+  auto it = m->step_graphs.find(key);
+  if (it == m->step_graphs.end()) {
+    if (m->step_graphs.size() > 64) {
+      for (auto& kv : m->step_graphs) cudaGraphExecDestroy(kv.second.exec);
+      m->step_graphs.clear();
+    }
+    const long before = c->launches;
+    cudaGraph_t graph = nullptr;
+    ALM_CHECK_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(c->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    ALM_CHECK_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    OmniModel::StepGraph sg{nullptr, c->launches - before};
+    c->launches = before;
+    cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) throw AlmError{ALM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)};
+    it = m->step_graphs.emplace(key, sg).first;
+  }
+  for (int i = 0; i < n; ++i) ALM_CHECK_CUDA(cudaGraphLaunch(it->second.exec, c->stream));
+  c->launches += it->second.launches * n;
+}
+
 }  // namespace
 
 void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
@@ -475,18 +544,21 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
   const size_t after_pt_tokens = ws.mark();
   {
     DecodeBufs u = alloc_decode(c, m, B, 1, Tpt - 1);
+    fill_i32(c, u.tpos, 1, 0);
+    HeadArgs off;
+    run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, n_prompt - 1, off);  // prompt tokens only fill the caches
+    HeadArgs h;
+    h.on = true; h.cfg = hc; h.tokens = pt_tok; h.tstride = Tpt; h.n_prompt_m1 = n_prompt - 1;
+    h.finished = finished; h.ntok = ntok; h.seqs_per_image = 1;
     std::vector<int> fin(B);
-    for (int t = 0; t < Tpt - 1; ++t) {
-      const int gen = t - (n_prompt - 1);
-      decoder_step(c, m, 0, u, pt_tok, Tpt, t, 0, B, gen >= 0);
-      if (gen >= 0) {
-        head_select(c, u.logits, B, m->V, m->V, (gen % 2 == 0) ? 0 : 1, hc, pt_tok, Tpt, t + 1, nullptr, 0, 0, finished,
-                    ntok, gen, 1);
-        if ((gen & 15) == 15 && t + 1 < Tpt - 1) {  // every image hit EOS?  (one small sync per 16 tokens)
-          ALM_CHECK_CUDA(cudaMemcpyAsync(fin.data(), finished, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-          ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-          if (std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; })) break;
-        }
+    for (int done = 0; done < cfg.pt_seq_length;) {
+      const int chunk = std::min(16, cfg.pt_seq_length - done);
+      run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, chunk, h);
+      done += chunk;
+      if (done < cfg.pt_seq_length) {  // every image hit EOS?  (one small sync per 16 tokens)
+        ALM_CHECK_CUDA(cudaMemcpyAsync(fin.data(), finished, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+        if (std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; })) break;
       }
     }
   }
@@ -522,16 +594,16 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
     fill_i32(c, tok, static_cast<long>(S) * T, 0);
     build_inst_prompts(c, pt_tok, Tpt, n_prompt, ntok, B, Ncap, phase == 1 ? cfg.poly_sos : cfg.rec_sos, tok, T);
     DecodeBufs u = alloc_decode(c, m, B, Ncap, T - 1);
-    for (int t = 0; t < T - 1; ++t) {
-      const int gen = t - 2;
-      decoder_step(c, m, phase, u, tok, T, t, 0, B, gen >= 0);
-      if (gen >= 0)
-        head_select(c, u.logits, S, m->V, m->V, phase == 1 ? 1 : 2, hc, tok, T, t + 1, probs, len, gen, nullptr, nullptr,
-                    gen, Ncap);
-    }
-    std::vector<int> h(static_cast<size_t>(S) * T);
+    fill_i32(c, u.tpos, 1, 0);
+    HeadArgs off;
+    run_steps(c, m, phase, u, tok, T, 0, B, 2, off);
+    HeadArgs h;
+    h.on = true; h.cfg = hc; h.tokens = tok; h.tstride = T; h.n_prompt_m1 = 2; h.probs = probs; h.pstride = len;
+    h.seqs_per_image = Ncap;
+    run_steps(c, m, phase, u, tok, T, 0, B, len, h);
+    std::vector<int> hh(static_cast<size_t>(S) * T);
     std::vector<float> hp(static_cast<size_t>(S) * len);
-    ALM_CHECK_CUDA(cudaMemcpyAsync(h.data(), tok, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaMemcpyAsync(hh.data(), tok, hh.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ALM_CHECK_CUDA(cudaMemcpyAsync(hp.data(), probs, hp.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
     for (int b = 0; b < B; ++b)
@@ -539,8 +611,8 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
         const size_t s = static_cast<size_t>(b) * Ncap + n;
         for (int k = 0; k < len; ++k) {
           const size_t o = (static_cast<size_t>(b) * maxI + n) * len + k;
-          if (phase == 1) poly[o] = h[s * T + 3 + k];
-          else { rec[o] = h[s * T + 3 + k]; rec_prob[o] = hp[s * len + k]; }
+          if (phase == 1) poly[o] = hh[s * T + 3 + k];
+          else { rec[o] = hh[s * T + 3 + k]; rec_prob[o] = hp[s * len + k]; }
         }
       }
   }
@@ -563,8 +635,10 @@ void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_s
   int* tok = ws.get<int>(h.size());
   ALM_CHECK_CUDA(cudaMemcpyAsync(tok, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   DecodeBufs u = alloc_decode(c, m, 1, n_seq, len);
+  fill_i32(c, u.tpos, 1, 0);
   for (int t = 0; t < len; ++t) {
-    decoder_step(c, m, kind, u, tok, len, t, image, 1, true);
+    decoder_step(c, m, kind, u, tok, len, image, 1, true);
+    add_i32(c, u.tpos, 1);
     // logits [n_seq, len, V] <- step t rows
     ALM_CHECK_CUDA(cudaMemcpy2DAsync(logits + static_cast<size_t>(t) * m->V, static_cast<size_t>(len) * m->V * sizeof(float),
                                      u.logits, static_cast<size_t>(m->V) * sizeof(float), static_cast<size_t>(m->V) * sizeof(float),

@@ -69,6 +69,12 @@ struct OmniModel {
   bf16 *kc_hi = nullptr, *kc_lo = nullptr;                // [B*M, 6144]
   bf16 *vt_hi = nullptr, *vt_lo = nullptr;                // [B, 6144, Mpad]
   size_t ws_mark = 0;                                     // arena offset after the encode-persistent buffers
+  // captured decode-step graphs, keyed by everything that determines the launch sequence and its pointers
+  struct StepGraph { cudaGraphExec_t exec; long launches; };
+  std::map<std::vector<long>, StepGraph> step_graphs;
+  ~OmniModel() {
+    for (auto& kv : step_graphs) cudaGraphExecDestroy(kv.second.exec);
+  }
 };
 
 void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t);
@@ -84,14 +90,15 @@ void nearest_map(Ctx* c, int* map, int B, int Hd, int Wd, int Hs, int Ws);
 void fpn_assemble(Ctx* c, const float* p2, const float* p3, const float* p4, const float* p5, int B, const int* Hs,
                   const int* Ws, int Ho, int Wo, bf16* hi, bf16* lo);
 void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, const float* dim_t, float* pos,
-              uint8_t* kpm);
-void embed_ln(Ctx* c, const int* tokens, int tstride, int t, int S, const float* word_emb, const float* pos_emb,
-              const float* gamma, const float* beta, float* x);
-void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, int t, int Tmax,
+              uint8_t* kpm, float* scratch);
+void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, const float* word_emb,
+              const float* pos_emb, const float* gamma, const float* beta, float* x, float* qpos);
+void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* tptr, int Tmax,
                     bf16* out_hi, bf16* out_lo);
-void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int mode, const HeadCfg& cfg, int* tokens,
-                 int tstride, int tnext, float* probs, int pstride, int pidx, int* finished, int* ntok, int gen_index,
+void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
+                 int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image);
+void add_i32(Ctx* c, int* p, int v);
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,
                         int sos, int* tokens, int tstride);
 void fill_i32(Ctx* c, int* p, long n, int v);

@@ -125,10 +125,11 @@ fpn_assemble_kernel(const float* __restrict__ p2, const float* __restrict__ p3, 
 }
 
 // Sine position embedding + key-padding mask at the memory resolution (position_embedding.py:24-44,
-// swin_transformer.py:622).  One CTA per image.  mask: u8 [B,H,W] or null.
+// swin_transformer.py:622).  Kernel 1 (one CTA per image): nearest-resized mask, cumulative sums, normalised
+// y/x embeddings.  Kernel 2 (elementwise over B*h*w*512): sin / cos.   mask: u8 [B,H,W] or null.
 __global__ void __launch_bounds__(256)
-sine_pos_kernel(const uint8_t* __restrict__ mask, int H, int W, int h, int w, const float* __restrict__ dim_t,
-                float* __restrict__ pos, uint8_t* __restrict__ kpm) {
+sine_embed_kernel(const uint8_t* __restrict__ mask, int H, int W, int h, int w, float* __restrict__ yemb,
+                  float* __restrict__ xemb, uint8_t* __restrict__ kpm) {
   extern __shared__ float sm[];
   float* ye = sm;           // [h*w] cumsum over rows
   float* xe = sm + h * w;   // [h*w] cumsum over cols
@@ -154,28 +155,40 @@ sine_pos_kernel(const uint8_t* __restrict__ mask, int H, int W, int h, int w, co
   }
   __syncthreads();
   const float two_pi = 6.283185307179586f;
-  for (long i = t; i < static_cast<long>(h) * w * 512; i += blockDim.x) {
-    const int c = static_cast<int>(i & 511);
-    const int px = static_cast<int>(i >> 9);
-    const int y = px / w, x = px % w;
-    float e;
-    int cc;
-    if (c < 256) { cc = c; e = ye[px] / (ye[(h - 1) * w + x] + 1e-6f) * two_pi; }
-    else { cc = c - 256; e = xe[px] / (xe[y * w + (w - 1)] + 1e-6f) * two_pi; }
-    const float a = e / dim_t[cc];
-    pos[(static_cast<long>(b) * h * w + px) * 512 + c] = (cc & 1) ? cosf(a) : sinf(a);
+  for (int i = t; i < h * w; i += blockDim.x) {
+    const int y = i / w, x = i % w;
+    yemb[static_cast<long>(b) * h * w + i] = ye[i] / (ye[(h - 1) * w + x] + 1e-6f) * two_pi;
+    xemb[static_cast<long>(b) * h * w + i] = xe[i] / (xe[y * w + (w - 1)] + 1e-6f) * two_pi;
   }
+}
+__global__ void sine_pos_kernel(const float* __restrict__ yemb, const float* __restrict__ xemb,
+                                const float* __restrict__ dim_t, long npix, float* __restrict__ pos) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * 512) return;
+  const int c = static_cast<int>(i & 511);
+  const long px = i >> 9;
+  const int cc = c & 255;
+  const float a = (c < 256 ? yemb[px] : xemb[px]) / dim_t[cc];
+  pos[i] = (cc & 1) ? cosf(a) : sinf(a);
 }
 
 // ----------------------------------------------------------------------------------------------- decoder
 // x[s] = LN(word_emb[tok[s, t]] + pos_emb[t])   (transformer.py:313-325).  One warp per sequence, d = 512.
 __global__ void __launch_bounds__(256)
-embed_ln_kernel(const int* __restrict__ tokens, int tstride, int t, int S, const float* __restrict__ word_emb,
-                const float* __restrict__ pos_emb, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float* __restrict__ x) {
+embed_ln_kernel(const int* __restrict__ tokens, int tstride, const int* __restrict__ tptr, int S,
+                const float* __restrict__ word_emb, const float* __restrict__ pos_emb, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ x, float* __restrict__ qpos) {
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
   const int lane = threadIdx.x & 31;
+  const int t = *tptr;  // device-side position counter: the same captured graph serves every token
+  if (s == 0) {         // query_pos of this step (transformer.py:328), read by every layer
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = 4 * (lane + 32 * j);
+      *reinterpret_cast<float4*>(qpos + e) = *reinterpret_cast<const float4*>(pos_emb + static_cast<long>(t) * 512 + e);
+    }
+  }
   const int tok = tokens[static_cast<long>(s) * tstride + t];
   float4 v[4];
   float sum = 0.f;
@@ -212,9 +225,10 @@ embed_ln_kernel(const int* __restrict__ tokens, int tstride, int t, int S, const
 // One warp per (sequence, head); head_dim 64; q is scaled by 1/8 first like nn.MultiheadAttention.
 __global__ void __launch_bounds__(128)
 self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vnew, float* __restrict__ kc,
-                      float* __restrict__ vc, int S, int t, int Tmax, bf16* __restrict__ out_hi,
+                      float* __restrict__ vc, int S, const int* __restrict__ tptr, int Tmax, bf16* __restrict__ out_hi,
                       bf16* __restrict__ out_lo) {
   extern __shared__ float sp[];  // [4 warps][Tmax]
+  const int t = *tptr;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long g = static_cast<long>(blockIdx.x) * 4 + wid;
   if (g >= static_cast<long>(S) * 8) return;
@@ -256,6 +270,7 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
   sum = warp_sum(sum);
   __syncwarp();
   float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
   for (int j = 0; j <= t; ++j) {
     const float pj = p[j] / sum;
     const float* vj = vc + (static_cast<long>(s) * Tmax + j) * 512 + h * 64;
@@ -269,15 +284,23 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
 }
 
 // Softmax over the first `nsoft` logits, zero the disallowed classes, top-1 (transformer.py:108-125,
-// 257-261, 273-280).  mode: 0 = bins + pt_eos, 1 = bins, 2 = chars (num_bins..recog_pad) + rec_eos,
-// 3 = last `vie` classes.  One CTA per sequence.  Writes tokens[s, t+1] and (optionally) prob / EOS state.
+// 257-261, 273-280).  phase 0 = pt loop (mode alternates with the generated-token index), 1 = poly (bins),
+// 2 = rec (chars num_bins..recog_pad + rec_eos).  One CTA per sequence.  Writes tokens[s, t+1] and (optionally)
+// prob / EOS state.  The position t comes from the device-side counter so that the step can be graph-replayed.
 __global__ void __launch_bounds__(256)
-head_select_kernel(const float* __restrict__ logits, int V, int nsoft, int mode, HeadCfg cfg, int* __restrict__ tokens,
-                   int tstride, int tnext, float* __restrict__ probs, int pstride, int pidx,
-                   int* __restrict__ finished, int* __restrict__ ntok, int gen_index, int seqs_per_image) {
+head_select_kernel(const float* __restrict__ logits, int V, int nsoft, int phase, HeadCfg cfg, int* __restrict__ tokens,
+                   int tstride, const int* __restrict__ tptr, int n_prompt_m1, float* __restrict__ probs, int pstride,
+                   int* __restrict__ finished, int* __restrict__ ntok, int seqs_per_image) {
   __shared__ float redf[8];
   __shared__ int redi[8];
   const int s = blockIdx.x, t = threadIdx.x;
+  const int pos_t = *tptr;
+  const int gen_index = pos_t - n_prompt_m1;  // index of the token being generated
+  const int tnext = pos_t + 1, pidx = gen_index;
+  // pt: even step = coordinate or EOS, odd = coordinate (transformer.py:110-115); KIE adds a class slot (:117-123)
+  int mode;
+  if (phase == 0) mode = cfg.vie ? (gen_index % 3 == 0 ? 0 : (gen_index % 3 == 1 ? 1 : 3)) : (gen_index % 2 == 0 ? 0 : 1);
+  else mode = phase;
   const float* x = logits + static_cast<long>(s) * V;
   float m = -INFINITY;
   for (int j = t; j < nsoft; j += 256) m = fmaxf(m, x[j]);
@@ -349,6 +372,8 @@ __global__ void build_inst_prompts_kernel(const int* __restrict__ pt_tokens, int
   row[2] = sos;
 }
 
+__global__ void add_i32_kernel(int* p, int v) { *p += v; }
+
 __global__ void fill_i32_kernel(int* p, long n, int v) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -379,23 +404,27 @@ void fpn_assemble(Ctx* c, const float* p2, const float* p3, const float* p4, con
   count_launch(c); check_launch("fpn_assemble");
 }
 void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, const float* dim_t, float* pos,
-              uint8_t* kpm) {
+              uint8_t* kpm, float* scratch /* 2*B*h*w floats */) {
   const size_t sm = static_cast<size_t>(2) * h * w * sizeof(float);
   ALM_REQUIRE(sm <= 200 * 1024, ALM_ERR_UNSUPPORTED, "sine_pos: memory grid too large for shared memory");
   static bool attr = false;
   if (!attr) {
-    ALM_CHECK_CUDA(cudaFuncSetAttribute(sine_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ALM_CHECK_CUDA(cudaFuncSetAttribute(sine_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  sine_pos_kernel<<<B, 256, sm, c->stream>>>(mask, H, W, h, w, dim_t, pos, kpm);
-  count_launch(c); check_launch("sine_pos");
+  const long npix = static_cast<long>(B) * h * w;
+  float* yemb = scratch;
+  float* xemb = scratch + npix;
+  sine_embed_kernel<<<B, 256, sm, c->stream>>>(mask, H, W, h, w, yemb, xemb, kpm);
+  sine_pos_kernel<<<static_cast<unsigned>((npix * 512 + 255) / 256), 256, 0, c->stream>>>(yemb, xemb, dim_t, npix, pos);
+  count_launch(c, 2); check_launch("sine_pos");
 }
-void embed_ln(Ctx* c, const int* tokens, int tstride, int t, int S, const float* word_emb, const float* pos_emb,
-              const float* gamma, const float* beta, float* x) {
-  embed_ln_kernel<<<(S + 7) / 8, 256, 0, c->stream>>>(tokens, tstride, t, S, word_emb, pos_emb, gamma, beta, x);
+void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, const float* word_emb,
+              const float* pos_emb, const float* gamma, const float* beta, float* x, float* qpos) {
+  embed_ln_kernel<<<(S + 7) / 8, 256, 0, c->stream>>>(tokens, tstride, tptr, S, word_emb, pos_emb, gamma, beta, x, qpos);
   count_launch(c); check_launch("embed_ln");
 }
-void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, int t, int Tmax,
+void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* t, int Tmax,
                     bf16* out_hi, bf16* out_lo) {
   const long groups = static_cast<long>(S) * 8;
   const size_t sm = static_cast<size_t>(4) * Tmax * sizeof(float);
@@ -403,11 +432,11 @@ void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float
                                                                                         out_hi, out_lo);
   count_launch(c); check_launch("self_attn_step");
 }
-void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int mode, const HeadCfg& cfg, int* tokens,
-                 int tstride, int tnext, float* probs, int pstride, int pidx, int* finished, int* ntok, int gen_index,
+void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
+                 int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image) {
-  head_select_kernel<<<S, 256, 0, c->stream>>>(logits, V, nsoft, mode, cfg, tokens, tstride, tnext, probs, pstride,
-                                               pidx, finished, ntok, gen_index, seqs_per_image);
+  head_select_kernel<<<S, 256, 0, c->stream>>>(logits, V, nsoft, phase, cfg, tokens, tstride, tptr, n_prompt_m1, probs,
+                                               pstride, finished, ntok, seqs_per_image);
   count_launch(c); check_launch("head_select");
 }
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,
@@ -415,6 +444,10 @@ void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_promp
   build_inst_prompts_kernel<<<(B * Ncap + 255) / 256, 256, 0, c->stream>>>(pt_tokens, pt_stride, n_prompt, ntok, B,
                                                                            Ncap, sos, tokens, tstride);
   count_launch(c); check_launch("build_inst_prompts");
+}
+void add_i32(Ctx* c, int* p, int v) {
+  add_i32_kernel<<<1, 1, 0, c->stream>>>(p, v);
+  count_launch(c); check_launch("add_i32");
 }
 void fill_i32(Ctx* c, int* p, long n, int v) {
   if (n == 0) return;

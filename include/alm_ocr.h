@@ -77,7 +77,9 @@ ALM_API const char* alm_last_error(const alm_ctx* ctx); /* valid until the next 
 ALM_API const char* alm_version(void);
 
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
- *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm". */
+ *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
+ *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
+ *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
 /* kernels launched on this context since the last call with reset != 0 */
 ALM_API long alm_launch_count(alm_ctx* ctx, int reset);

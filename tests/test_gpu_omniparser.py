@@ -101,10 +101,13 @@ def test_window_attention_core(ctx, B, nWh, nWw, heads, shift):
         attn = (attn.view(B, nWh * nWw, heads, 49, 49) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, 49, 49)
     ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(rows, C)
     qd, td = qkv.cuda(), tab.cuda()
-    out = torch.empty(rows, C, device='cuda')
-    ctx.check(ctx.lib.alm_op_window_attention(ctx.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, C, heads,
-                                              shift))
-    assert float((out.cpu() - ref).abs().max()) < 5e-6
+    for impl, tol in ((0, 5e-5), (1, 5e-6)):  # tensor-core (split bf16) kernel and the fp32 SIMT debug kernel
+        ctx.set_option('wattn_impl', impl)
+        out = torch.full((rows, C), float('nan'), device='cuda')
+        ctx.check(ctx.lib.alm_op_window_attention(ctx.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, C,
+                                                  heads, shift))
+        assert float((out.cpu() - ref).abs().max()) < tol, impl
+    ctx.set_option('wattn_impl', 0)
 
 
 # ----------------------------------------------------------------------------------------------- model

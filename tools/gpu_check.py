@@ -129,9 +129,27 @@ def g_wattn():
             attn = attn.view(-1, heads, 49, 49)
         ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(rows, Cc)
         qd, td = qkv.cuda(), tab.cuda()
+        for impl in (0, 1):
+            c.set_option('wattn_impl', impl)
+            out = torch.full((rows, Cc), float('nan'), device='cuda')
+            c.check(c.lib.alm_op_window_attention(c.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, Cc, heads, shift))
+            print(f'window_attention impl={impl} B={B} nW={nWh}x{nWw} heads={heads} shift={shift}: {_err(out.cpu(), ref)}')
+    # timing at the stage-0 / stage-2 sizes of config 2 (batch 16, 1024^2)
+    for (B, nW, heads) in [(16, 37, 4), (16, 10, 16)]:
+        Cc = heads * 32
+        rows = B * nW * nW * 49
+        qd = torch.randn(rows, 3 * Cc, device='cuda')
+        td = torch.randn(169, heads, device='cuda')
         out = torch.empty(rows, Cc, device='cuda')
-        c.check(c.lib.alm_op_window_attention(c.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, Cc, heads, shift))
-        print(f'window_attention B={B} nW={nWh}x{nWw} heads={heads} shift={shift}: {_err(out.cpu(), ref)}')
+        for impl in (0, 1):
+            c.set_option('wattn_impl', impl)
+            for _ in range(2):
+                c.check(c.lib.alm_op_window_attention(c.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nW, nW, Cc, heads, 3))
+            torch.cuda.synchronize(); t0 = time.time()
+            for _ in range(5):
+                c.check(c.lib.alm_op_window_attention(c.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nW, nW, Cc, heads, 3))
+            torch.cuda.synchronize()
+            print(f'window_attention timing impl={impl} B={B} nW={nW}^2 heads={heads}: {(time.time() - t0) / 5 * 1e3:.3f} ms', flush=True)
 
 
 def _enc(impl):
