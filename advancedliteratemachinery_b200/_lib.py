@@ -45,6 +45,7 @@ SIGNATURES = {
     'alm_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
     'alm_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+    'alm_trace_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     'alm_bench_gemm': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     'alm_load_weights': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorDesc), C.c_int]),
     'alm_omni_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -106,6 +107,13 @@ class Context:
         ms, fl, n = C.c_double(), C.c_double(), C.c_long()
         self.check(self.lib.alm_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
+
+    def trace_read(self, max_records=200000):
+        import numpy as np
+        buf = np.zeros((max_records, 6), dtype=np.uint64)
+        n = C.c_int()
+        self.check(self.lib.alm_trace_read(self.h, buf.ctypes.data, max_records, C.byref(n)))
+        return buf[:n.value]
 
     def bench_gemm(self, M, N, K, iters=20) -> float:
         ms = C.c_float()

@@ -153,6 +153,9 @@ struct Ctx {
   };
   std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
   int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps
+  unsigned long long* trace_buf = nullptr;  // optional in-kernel GEMM timeline (alm_set_option "trace_gemm")
+  int* trace_idx = nullptr;
+  int trace_cap = 0;
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;

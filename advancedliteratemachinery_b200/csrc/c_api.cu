@@ -158,6 +158,14 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "gemm_impl") {
       ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "gemm_impl must be 0 or 1");
       h->c.gemm_impl = static_cast<int>(value);
+    } else if (k == "trace_gemm") {
+      if (h->c.trace_buf) { cudaFree(h->c.trace_buf); cudaFree(h->c.trace_idx); h->c.trace_buf = nullptr; h->c.trace_idx = nullptr; }
+      h->c.trace_cap = static_cast<int>(value);
+      if (value > 0) {
+        ALM_CHECK_CUDA(cudaMalloc(&h->c.trace_buf, static_cast<size_t>(value) * 6 * sizeof(unsigned long long)));
+        ALM_CHECK_CUDA(cudaMalloc(&h->c.trace_idx, sizeof(int)));
+        ALM_CHECK_CUDA(cudaMemset(h->c.trace_idx, 0, sizeof(int)));
+      }
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
     } else if (k == "use_graphs") {
@@ -196,6 +204,19 @@ int alm_profile_read(alm_ctx* h, double* gemm_ms, double* gemm_flops, long* gemm
     if (gemm_flops) *gemm_flops = fl;
     if (gemm_launches) *gemm_launches = static_cast<long>(h->c.gemm_recs.size());
     h->c.gemm_recs.clear();
+  });
+}
+
+int alm_trace_read(alm_ctx* h, unsigned long long* out, int max_records, int* n_records) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(h->c.trace_buf && out && n_records, ALM_ERR_STATE, "trace_gemm is not enabled");
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+    int n = 0;
+    ALM_CHECK_CUDA(cudaMemcpy(&n, h->c.trace_idx, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::min(n, std::min(h->c.trace_cap, max_records));
+    ALM_CHECK_CUDA(cudaMemcpy(out, h->c.trace_buf, static_cast<size_t>(n) * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    ALM_CHECK_CUDA(cudaMemset(h->c.trace_idx, 0, sizeof(int)));
+    *n_records = n;
   });
 }
 

@@ -28,6 +28,7 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
+constexpr int kMaxStages = 16;
 
 struct GemmParams {
   int M, N, K;
@@ -38,6 +39,13 @@ struct GemmParams {
   long num_tiles;
   Epilogue e;
   int vec_ok;  // rows are 16-byte addressable -> vector stores
+  int stage_tx;               // bytes one pipeline stage receives (the A box shrinks to the live rows when M < 128)
+  int a_bytes;                // shared-memory footprint of one A operand tile (live rows only)
+  int stage_bytes;            // one stage: kNumA A tiles + kNumB B tiles
+  int stages;                 // pipeline depth: as many stages as fit (<= 16) -- deep for the small-M decode GEMMs
+  unsigned long long* trace;  // optional [cap][6] records: start ns, end ns (CTA 0), M, N, K, tiles
+  int* trace_idx;
+  int trace_cap;
 };
 
 template <int BLOCK_N, int NSPLIT>
@@ -51,10 +59,21 @@ struct SmemLayout {
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // one XOR-swizzled 32x32 fp32 block per epilogue warp
   static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotal = kBudget + kBarBytes + kStagingBytes + 1024;  // +1024 alignment slack
 };
 
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), exact-erf form (nn.GELU default).  erff() is the CUDA libdevice
+// implementation (<= 2 ulp); this is the issue-bound part of the fc1 epilogue, kept exact on purpose: a cheaper
+// erf approximation would sit at ~1e-7 absolute, which is fine numerically, but is left for a later round.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// (x, y) -> packed bf16x2 hi and lo words with one cvt.rn.bf16x2.f32 each (hi + lo == x to ~2^-17)
+__device__ __forceinline__ void split_pack_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));  // upper half <- first source
+  const float rx = x - __uint_as_float(hi << 16);
+  const float ry = y - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
 
 template <int BLOCK_N, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -65,14 +84,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
-  uint64_t* empty_bar = full_bar + L::kStages;
-  uint64_t* tmem_full = empty_bar + L::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBudget);  // operand stages live in [0, kBudget)
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  int trace_slot = -1;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    trace_slot = atomicAdd(p.trace_idx, 1);
+    if (trace_slot < p.trace_cap) {
+      unsigned long long* r = p.trace + 6 * static_cast<long>(trace_slot);
+      r[0] = ptx::globaltimer_ns(); r[2] = p.M; r[3] = p.N; r[4] = p.K; r[5] = p.num_tiles * 1000 + BLOCK_N;
+    } else trace_slot = -1;
+  }
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two >= 32)
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
@@ -83,7 +110,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       ptx::prefetch_tmap(&tm_a_lo);
       ptx::prefetch_tmap(&tm_b_lo);
     }
-    for (int s = 0; s < L::kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
@@ -115,16 +142,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const int w0 = p.b_b0 ? b0 : 0, w1 = p.b_b1 ? b1 : 0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = stage_base + stage * L::kStageBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          uint8_t* st = stage_base + stage * p.stage_bytes;
+          ptx::mbar_expect_tx(&full_bar[stage], p.stage_tx);
           ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
           if (NSPLIT == 3)
-            ptx::tma_load_4d(st + L::kABytes, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
-          uint8_t* sb = st + L::kNumA * L::kABytes;
+            ptx::tma_load_4d(st + p.a_bytes, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
+          uint8_t* sb = st + L::kNumA * p.a_bytes;
           ptx::tma_load_4d(sb, &tm_b_hi, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
           if (NSPLIT == 3)
             ptx::tma_load_4d(sb + L::kBBytes, &tm_b_lo, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
-          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -145,9 +172,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(stage_base + stage * L::kStageBytes);
-          const uint32_t a_lo = a_hi + L::kABytes;
-          const uint32_t b_hi = a_hi + L::kNumA * L::kABytes;
+          const uint32_t a_hi = ptx::smem_u32(stage_base + stage * p.stage_bytes);
+          const uint32_t a_lo = a_hi + p.a_bytes;
+          const uint32_t b_hi = a_hi + L::kNumA * p.a_bytes;
           const uint32_t b_lo = b_hi + L::kBBytes;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -163,7 +190,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -176,7 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // thread / eight threads per row, so that every global access (bias, residual, outputs) is a full 128 B line.
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
     const int half = (warp - 2) >> 2;      // 32-column chunks c = half, half + 2, ... of the tile
-    float* stg = reinterpret_cast<float*>(smem + L::kStages * L::kStageBytes + L::kBarBytes) + (warp - 2) * 1024;
+    float* stg = reinterpret_cast<float*>(smem + L::kBudget + L::kBarBytes) + (warp - 2) * 1024;
     const Epilogue& e = p.e;
     const int rl_base = lane >> 3, j4 = lane & 7;
     int as = 0;
@@ -207,28 +234,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         const int col = col0 + j4 * 4;
-#pragma unroll 2
+        const bool col_ok = col < p.N;
+        const bool vec = p.vec_ok && col + 3 < p.N;
+        // phase 1: everything this thread needs for its 8 rows is requested up front (independent loads in
+        // flight: staging reads, row maps, residual lines) -- the epilogue is latency-bound otherwise.
+        float4 acc[8];
+        int orow[8], rrow[8];
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rl_base;
+          acc[i] = *reinterpret_cast<const float4*>(stg + rl * 32 + ((j4 ^ (rl & 7)) << 2));
           const int row = row_base + rl;
-          const float4 acc = *reinterpret_cast<const float4*>(stg + rl * 32 + ((j4 ^ (rl & 7)) << 2));
-          if (row >= p.M || col >= p.N) continue;
-          long orow = row;
-          if (e.out_map) orow = e.out_map[row];
-          if (orow < 0) continue;
-          long rrow = orow;
-          if (e.resid_map) rrow = e.resid_map[row];
-          const long o = obatch + orow * e.ldo + col;
-          float f[4] = {acc.x * e.alpha, acc.y * e.alpha, acc.z * e.alpha, acc.w * e.alpha};
+          int o = (row < p.M && col_ok) ? row : -1;
+          if (o >= 0 && e.out_map) o = e.out_map[row];
+          orow[i] = o;
+          rrow[i] = (o >= 0 && e.resid_map) ? e.resid_map[row] : o;
+        }
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec && bias && e.bias_mode == BIAS_COL) bb = *reinterpret_cast<const float4*>(bias + col);
+        float4 res[8];
+        if (rbatch && vec) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            res[i] = rrow[i] >= 0 ? *reinterpret_cast<const float4*>(rbatch + static_cast<long>(rrow[i]) * e.ldr + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // phase 2: math + stores
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (orow[i] < 0) continue;
+          const int row = row_base + i * 4 + rl_base;
+          const long o = obatch + static_cast<long>(orow[i]) * e.ldo + col;
+          float f[4] = {acc[i].x * e.alpha, acc[i].y * e.alpha, acc[i].z * e.alpha, acc[i].w * e.alpha};
           if (bias && e.bias_mode == BIAS_ROW) {
             const float rb = bias[row];
             f[0] += rb; f[1] += rb; f[2] += rb; f[3] += rb;
           }
-          if (p.vec_ok && col + 3 < p.N) {
-            if (bias && e.bias_mode == BIAS_COL) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + col);
-              f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
-            }
+          if (vec) {
+            f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
             if (e.act == ACT_GELU) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) f[q] = gelu_erf(f[q]);
@@ -236,16 +279,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
               for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.0f);
             }
-            if (rbatch) {
-              const float4 rr = *reinterpret_cast<const float4*>(rbatch + rrow * e.ldr + col);
-              f[0] += rr.x; f[1] += rr.y; f[2] += rr.z; f[3] += rr.w;
-            }
+            if (rbatch) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
             if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(f[0], f[1], f[2], f[3]);
             if (e.out_hi) {
-              bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-              split_bf16(f[0], h0, l0); split_bf16(f[1], h1, l1); split_bf16(f[2], h2, l2); split_bf16(f[3], h3, l3);
-              *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-              if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+              uint32_t h01, l01, h23, l23;
+              split_pack_bf16x2(f[0], f[1], h01, l01);
+              split_pack_bf16x2(f[2], f[3], h23, l23);
+              *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(h01, h23);
+              if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(l01, l23);
             }
           } else {
             // ragged / unaligned tail: scalar, guarded
@@ -256,7 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               if (bias && e.bias_mode == BIAS_COL) x += bias[col + q];
               if (e.act == ACT_GELU) x = gelu_erf(x);
               else if (e.act == ACT_RELU) x = fmaxf(x, 0.0f);
-              if (rbatch) x += rbatch[rrow * e.ldr + col + q];
+              if (rbatch) x += rbatch[static_cast<long>(rrow[i]) * e.ldr + col + q];
               if (e.out_f32) e.out_f32[o + q] = x;
               if (e.out_hi) {
                 bf16 h, l;
@@ -283,6 +324,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (trace_slot >= 0) p.trace[6 * static_cast<long>(trace_slot) + 1] = ptx::globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,9 +431,16 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   }
   p.n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_tiles = static_cast<long>(p.m_blocks) * p.n_blocks * p.nb0 * p.nb1;
-  const CUtensorMap ta_hi = make_tmap(c, A.hi, A, BLOCK_M);  // by value: the cache may be cleared by a later call
+  // rows of A beyond M are never stored, so the TMA box only covers the live rows (multiple of 8 = one swizzle
+  // group); the MMA still reads 128 rows of shared memory, the stale ones only feed discarded accumulator rows.
+  const int a_rows = std::min(BLOCK_M, (p.M + 7) & ~7);
+  p.a_bytes = a_rows * BLOCK_K * 2;
+  p.stage_bytes = L::kNumA * p.a_bytes + L::kNumB * L::kBBytes;
+  p.stage_tx = p.stage_bytes;
+  p.stages = std::min(kMaxStages, L::kBudget / p.stage_bytes);
+  const CUtensorMap ta_hi = make_tmap(c, A.hi, A, a_rows);  // by value: the cache may be cleared by a later call
   const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N);
-  const CUtensorMap ta_lo = (NSPLIT == 3) ? make_tmap(c, A.lo, A, BLOCK_M) : ta_hi;
+  const CUtensorMap ta_lo = (NSPLIT == 3) ? make_tmap(c, A.lo, A, a_rows) : ta_hi;
   const CUtensorMap tb_lo = (NSPLIT == 3) ? make_tmap(c, B.lo, B, BLOCK_N) : tb_hi;
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, c->num_sms));
   kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
@@ -423,6 +472,7 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
                      (reinterpret_cast<uintptr_t>(E.resid) % 16 == 0);
   if (E.bias && E.bias_mode == BIAS_COL) vec = vec && (reinterpret_cast<uintptr_t>(E.bias) % 16 == 0) && (E.bias_bs0 % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
+  p.trace = c->trace_buf; p.trace_idx = c->trace_idx; p.trace_cap = c->trace_cap;
   const int nsplit = c->nsplit;
   ALM_REQUIRE(nsplit == 1 || (A.lo && B.lo), ALM_ERR_INVALID, "gemm: split mode needs lo operands");
 

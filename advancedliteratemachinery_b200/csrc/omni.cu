@@ -328,11 +328,17 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   SplitBuf mem = alloc_split(c, BM * 512), memp = alloc_split(c, BM * 512);
   gather_ln(c, m->memory, 512, nullptr, 1, 512, BM, nullptr, nullptr, 0.f, false, m->pos, 512, nullptr, 0, mem.hi,
             mem.lo, 512, memp.hi, memp.lo);
-  {  // K_c[b*M + m, dl*512 + f] = (memory + pos) Wk^T + bk for all 12 (decoder, layer) pairs at once
+  {  // K_c[b][dl][h][m][64] = (memory + pos) Wk^T + bk for all 12 (decoder, layer) pairs: head-major so that the keys
+     // of one (image, layer, head) are one contiguous 128-byte-row block (the per-token decode streams exactly that)
+    Operand a = act_op(memp.hi, memp.lo, m->M, 512, 512);
+    a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
+    Operand w = m->ca_k_all.w.op();
+    w.rows = 64; w.nb0 = 96; w.bs0 = static_cast<long>(64) * 512;
     Epilogue e;
-    e.out_hi = m->kc_hi; e.out_lo = m->kc_lo; e.ldo = 6144;
-    e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL;
-    gemm(c, act_op(memp.hi, memp.lo, BM, 512, 512), m->ca_k_all.w.op(), e);
+    e.out_hi = m->kc_hi; e.out_lo = m->kc_lo; e.ldo = 64;
+    e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
+    e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
+    gemm(c, a, w, e);
   }
   {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
     Operand bop = act_op(mem.hi, mem.lo, m->M, 512, 512);
@@ -355,7 +361,10 @@ struct DecodeBufs {
   float* qpos = nullptr;  // [512] query_pos of the current step
   int* tpos = nullptr;    // device-side position counter (so one captured graph serves every token)
   SplitBuf ln, lnp, att, q, o, hid, h0, h1;
-  float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr;
+  float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr, *qf = nullptr;
+  float* xq_partial = nullptr;  // fused single-query cross-attention: split partials + counters
+  int* xq_counters = nullptr;
+  int xq_splits = 1;
   SplitBuf prob;
   float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
   float* vc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -378,8 +387,16 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
   d.h1 = alloc_split(c, S * 512);
   d.qk = c->ws.get<float>(S * 1024);
   d.v = c->ws.get<float>(S * 512);
-  d.scores = c->ws.get<float>(S * 8 * m->Mpad);
-  d.prob = alloc_split(c, S * 8 * m->Mpad);
+  d.qf = c->ws.get<float>(S * 512);
+  if (Ncap == 1) {
+    d.xq_splits = cross_attn_q1_splits(c, B, m->M);
+    d.xq_partial = c->ws.get<float>(static_cast<size_t>(B) * 8 * d.xq_splits * 66);
+    d.xq_counters = c->ws.get<int>(static_cast<size_t>(B) * 8);
+    fill_i32(c, d.xq_counters, static_cast<long>(B) * 8, 0);
+  } else {
+    d.scores = c->ws.get<float>(S * 8 * m->Mpad);
+    d.prob = alloc_split(c, S * 8 * m->Mpad);
+  }
   d.logits = c->ws.get<float>(S * m->V);
   for (int l = 0; l < 4; ++l) {
     d.kc[l] = c->ws.get<float>(S * Tmax * 512);
@@ -409,29 +426,39 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     // --- cross attention against the per-image cached K / V^T
     gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n2.g, w.n2.b, 1e-5f, false, qpos, 0, nullptr, 0, nullptr, nullptr, 512,
               u.lnp.hi, u.lnp.lo);
-    linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
-    {
-      Operand a = act_op(u.q.hi, u.q.lo, Ncap, 64, 512);
-      a.nb0 = 8; a.bs0 = 64; a.nb1 = nimg; a.bs1 = static_cast<long>(Ncap) * 512;
-      const long koff = static_cast<long>(img0) * M * 6144 + dl * 512;
-      Operand k = act_op(m->kc_hi + koff, m->kc_lo + koff, M, 64, 6144);
-      k.nb0 = 8; k.bs0 = 64; k.nb1 = nimg; k.bs1 = static_cast<long>(M) * 6144;
-      Epilogue e;
-      e.out_f32 = u.scores; e.ldo = Mpad; e.obs0 = static_cast<long>(Ncap) * Mpad; e.obs1 = static_cast<long>(8) * Ncap * Mpad;
-      e.alpha = 0.125f;  // == scaling q by 64^-0.5 before q k^T (exact: power of two)
-      gemm(c, a, k, e);
-    }
-    softmax_rows(c, u.scores, Mpad, static_cast<long>(S) * 8, M, m->kpm + static_cast<long>(img0) * M, 8 * Ncap, M,
-                 nullptr, u.prob.hi, u.prob.lo, Mpad);
-    {
-      Operand a = act_op(u.prob.hi, u.prob.lo, Ncap, M, Mpad);
-      a.nb0 = 8; a.bs0 = static_cast<long>(Ncap) * Mpad; a.nb1 = nimg; a.bs1 = static_cast<long>(8) * Ncap * Mpad;
+    if (Ncap == 1) {
+      // one query per image: fused scores + mask + softmax + P.V, K/V streamed once (HBM-bound)
+      linear(c, u.lnp, S, w.ca_q, ACT_NONE, u.qf, nullptr);
+      const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
-      Operand v = act_op(m->vt_hi + voff, m->vt_lo + voff, 64, M, Mpad);
-      v.nb0 = 8; v.bs0 = static_cast<long>(64) * Mpad; v.nb1 = nimg; v.bs1 = static_cast<long>(6144) * Mpad;
-      Epilogue e;
-      e.out_hi = u.o.hi; e.out_lo = u.o.lo; e.ldo = 512; e.obs0 = 64; e.obs1 = static_cast<long>(Ncap) * 512;
-      gemm(c, a, v, e);
+      cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                    m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, u.o.hi,
+                    u.o.lo);
+    } else {
+      linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
+      {
+        Operand a = act_op(u.q.hi, u.q.lo, Ncap, 64, 512);
+        a.nb0 = 8; a.bs0 = 64; a.nb1 = nimg; a.bs1 = static_cast<long>(Ncap) * 512;
+        const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
+        Operand k = act_op(m->kc_hi + koff, m->kc_lo + koff, M, 64, 64);
+        k.nb0 = 8; k.bs0 = static_cast<long>(M) * 64; k.nb1 = nimg; k.bs1 = static_cast<long>(96) * M * 64;
+        Epilogue e;
+        e.out_f32 = u.scores; e.ldo = Mpad; e.obs0 = static_cast<long>(Ncap) * Mpad; e.obs1 = static_cast<long>(8) * Ncap * Mpad;
+        e.alpha = 0.125f;  // == scaling q by 64^-0.5 before q k^T (exact: power of two)
+        gemm(c, a, k, e);
+      }
+      softmax_rows(c, u.scores, Mpad, static_cast<long>(S) * 8, M, m->kpm + static_cast<long>(img0) * M, 8 * Ncap, M,
+                   nullptr, u.prob.hi, u.prob.lo, Mpad);
+      {
+        Operand a = act_op(u.prob.hi, u.prob.lo, Ncap, M, Mpad);
+        a.nb0 = 8; a.bs0 = static_cast<long>(Ncap) * Mpad; a.nb1 = nimg; a.bs1 = static_cast<long>(8) * Ncap * Mpad;
+        const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
+        Operand v = act_op(m->vt_hi + voff, m->vt_lo + voff, 64, M, Mpad);
+        v.nb0 = 8; v.bs0 = static_cast<long>(64) * Mpad; v.nb1 = nimg; v.bs1 = static_cast<long>(6144) * Mpad;
+        Epilogue e;
+        e.out_hi = u.o.hi; e.out_lo = u.o.lo; e.ldo = 512; e.obs0 = 64; e.obs1 = static_cast<long>(Ncap) * 512;
+        gemm(c, a, v, e);
+      }
     }
     linear(c, u.o, S, w.ca_out, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
     // --- FFN
@@ -481,7 +508,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf)};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {

@@ -66,7 +66,7 @@ struct OmniModel {
   float* memory = nullptr;                                // [B*M,512]
   float* pos = nullptr;                                   // [B*M,512]
   uint8_t* kpm = nullptr;                                 // [B*M]
-  bf16 *kc_hi = nullptr, *kc_lo = nullptr;                // [B*M, 6144]
+  bf16 *kc_hi = nullptr, *kc_lo = nullptr;                // [B, 12 (dec,layer), 8 heads, M, 64]
   bf16 *vt_hi = nullptr, *vt_lo = nullptr;                // [B, 6144, Mpad]
   size_t ws_mark = 0;                                     // arena offset after the encode-persistent buffers
   // captured decode-step graphs, keyed by everything that determines the launch sequence and its pointers
@@ -98,6 +98,10 @@ void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float
 void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
                  int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image);
+void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo,
+                   const uint8_t* kpm, int nimg, int M, int Mpad, float* partial, int* counters, int nsplit,
+                   bf16* out_hi, bf16* out_lo);
+int cross_attn_q1_splits(Ctx* c, int nimg, int M);
 void add_i32(Ctx* c, int* p, int v);
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,
                         int sos, int* tokens, int tstride);

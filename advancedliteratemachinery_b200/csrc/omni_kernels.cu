@@ -1,6 +1,8 @@
 // OmniParser-specific small kernels: window / merge / upsample index maps, FPN consumer-side assembly,
 // sine position embedding, and the per-token decoder kernels (embedding, cached self-attention, vocabulary
 // head selection).  All latency-/HBM-bound integer+fp32 work.
+#include <algorithm>
+
 #include "alm_internal.h"
 #include "omni.h"
 #include "ptx.cuh"
@@ -283,6 +285,159 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
   split_bf16(o1, hh, ll); out_hi[o + lane + 32] = hh; if (out_lo) out_lo[o + lane + 32] = ll;
 }
 
+// Fused single-query cross-attention for the pt loop (one live sequence per image, transformer.py:444-447):
+// scores = (q / 8) . K_c^T over the M memory tokens of the image, key-padding mask, softmax, P . V_c -- without
+// materialising the [S*8, M] score / probability matrices.  K_c / V_c^T are the cached split-bf16 projections
+// (hi + lo re-joined to fp32 on load, so the arithmetic is fp32 FMA).  HBM-bound: every (image, head) streams
+// its 2 x M x 64 x 4 B of K and V exactly once per layer-step.
+//   grid (nimg * 8, nsplit); split partials are merged by the last CTA of each (image, head) (self-resetting
+//   counter), so a single launch suffices.
+constexpr int XQ_THREADS = 256;
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, float (&o)[8]) {
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    o[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(XQ_THREADS)
+cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo,
+                     const bf16* __restrict__ vt_hi, const bf16* __restrict__ vt_lo, const uint8_t* __restrict__ kpm,
+                     int M, int Mpad, int keys_per_split, float* __restrict__ partial, int* __restrict__ counters,
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  extern __shared__ float xs[];            // [keys_per_split] scores / probabilities
+  __shared__ float sq[64];
+  __shared__ float red[XQ_THREADS / 32];
+  __shared__ float so[64];
+  __shared__ int last_flag;
+  const int pair = blockIdx.x, img = pair >> 3, h = pair & 7, split = blockIdx.y, nsplit = gridDim.y;
+  const int t = threadIdx.x;
+  const int k0 = split * keys_per_split, k1 = min(M, k0 + keys_per_split), nk = max(0, k1 - k0);
+  if (t < 64) sq[t] = q[static_cast<long>(img) * 512 + h * 64 + t] * 0.125f;  // q scaled first (functional.py MHA)
+  __syncthreads();
+  // ---- scores: 8 lanes per key (8 dims = 16 B of hi + 16 B of lo each), 4 keys per warp instruction ->
+  //      every K_c row is fetched as one coalesced 128-byte line per operand
+  float lmax = -INFINITY;
+  {
+    const int lane = t & 31, wid = t >> 5, sub = lane & 7, kq = lane >> 3;
+    float qd[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qd[e] = sq[8 * sub + e];
+    const long kbase = ((static_cast<long>(img) * 96 + h) * M + k0) * 64 + 8 * sub;  // K_c[img][dl(base)][h][key][64]
+#pragma unroll 4
+    for (int kb = wid * 4; kb < nk; kb += (XQ_THREADS / 32) * 4) {  // warp-uniform trip count (shuffles inside)
+      const int kk = kb + kq;
+      const bool live = kk < nk;
+      float a = 0.f;
+      if (live) {
+        const uint4 vh = *reinterpret_cast<const uint4*>(kc_hi + kbase + static_cast<long>(kk) * 64);
+        const uint4 vl = *reinterpret_cast<const uint4*>(kc_lo + kbase + static_cast<long>(kk) * 64);
+        float kf[8];
+        bf16x8_to_f32(vh, vl, kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(qd[e], kf[e], a);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (live && sub == 0) {
+        if (kpm && kpm[static_cast<long>(img) * M + k0 + kk]) a = -INFINITY;
+        xs[kk] = a;
+        lmax = fmaxf(lmax, a);
+      }
+    }
+  }
+  lmax = warp_max(lmax);
+  if ((t & 31) == 0) red[t >> 5] = lmax;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int i = 1; i < XQ_THREADS / 32; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int kk = t; kk < nk; kk += XQ_THREADS) {
+    const float e = (m == -INFINITY) ? 0.f : expf(xs[kk] - m);
+    xs[kk] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if ((t & 31) == 0) red[t >> 5] = lsum;
+  __syncthreads();
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < XQ_THREADS / 32; ++i) l += red[i];
+  // ---- o[d] = sum_k p_k V[k][d] : warp w owns dims 8w..8w+7; lanes span 256 consecutive keys of a V^T row per
+  //      step (coalesced 512-byte loads), probabilities come from shared memory; warp reduction per dim.
+  {
+    const int lane = t & 31, wid = t >> 5;
+    const int nk8 = (nk + 7) >> 3;  // groups of 8 keys (p = 0 beyond nk)
+    for (int kk = nk + t; kk < nk8 * 8; kk += XQ_THREADS) xs[kk] = 0.f;
+    __syncthreads();
+#pragma unroll 2
+    for (int dd = 0; dd < 8; ++dd) {
+      const int dim = wid * 8 + dd;
+      const long vrow = (static_cast<long>(img) * 6144 + h * 64 + dim) * Mpad + k0;
+      float acc = 0.f;
+#pragma unroll 2
+      for (int gidx = lane; gidx < nk8; gidx += 32) {
+        const uint4 vh = *reinterpret_cast<const uint4*>(vt_hi + vrow + 8 * gidx);
+        const uint4 vl = *reinterpret_cast<const uint4*>(vt_lo + vrow + 8 * gidx);
+        const float4 p0 = *reinterpret_cast<const float4*>(xs + 8 * gidx);
+        const float4 p1 = *reinterpret_cast<const float4*>(xs + 8 * gidx + 4);
+        float vf[8];
+        bf16x8_to_f32(vh, vl, vf);
+        acc = fmaf(p0.x, vf[0], acc); acc = fmaf(p0.y, vf[1], acc); acc = fmaf(p0.z, vf[2], acc); acc = fmaf(p0.w, vf[3], acc);
+        acc = fmaf(p1.x, vf[4], acc); acc = fmaf(p1.y, vf[5], acc); acc = fmaf(p1.z, vf[6], acc); acc = fmaf(p1.w, vf[7], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) so[dim] = acc;
+    }
+    __syncthreads();
+  }
+  const int d = t, part = (t < 64) ? 0 : 1;  // threads 0..63 publish one dim each
+  const float acc = (t < 64) ? so[t] : 0.f;
+  const long obase = static_cast<long>(img) * 512 + h * 64;
+  if (nsplit == 1) {
+    if (part == 0) {
+      bf16 hh, ll;
+      split_bf16(acc / l, hh, ll);
+      out_hi[obase + d] = hh;
+      if (out_lo) out_lo[obase + d] = ll;
+    }
+    return;
+  }
+  // ---- multi-split: publish (m, l, o[64]); the last CTA of the pair merges
+  float* my = partial + (static_cast<long>(pair) * nsplit + split) * 66;
+  if (part == 0) my[2 + d] = acc;
+  if (t == 0) { my[0] = m; my[1] = l; }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last_flag = (atomicAdd(&counters[pair], 1) == nsplit - 1);
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  if (t < 64) {
+    const float* base = partial + static_cast<long>(pair) * nsplit * 66;
+    float mm = -INFINITY;
+    for (int sidx = 0; sidx < nsplit; ++sidx) mm = fmaxf(mm, base[sidx * 66]);
+    float ltot = 0.f, otot = 0.f;
+    for (int sidx = 0; sidx < nsplit; ++sidx) {
+      const float ms = base[sidx * 66];
+      const float w = (ms == -INFINITY) ? 0.f : expf(ms - mm);
+      ltot += w * base[sidx * 66 + 1];
+      otot += w * base[sidx * 66 + 2 + t];
+    }
+    bf16 hh, ll;
+    split_bf16(otot / ltot, hh, ll);
+    out_hi[obase + t] = hh;
+    if (out_lo) out_lo[obase + t] = ll;
+  }
+  if (t == 0) counters[pair] = 0;  // ready for the next launch
+}
+
 // Softmax over the first `nsoft` logits, zero the disallowed classes, top-1 (transformer.py:108-125,
 // 257-261, 273-280).  phase 0 = pt loop (mode alternates with the generated-token index), 1 = poly (bins),
 // 2 = rec (chars num_bins..recog_pad + rec_eos).  One CTA per sequence.  Writes tokens[s, t+1] and (optionally)
@@ -444,6 +599,29 @@ void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_promp
   build_inst_prompts_kernel<<<(B * Ncap + 255) / 256, 256, 0, c->stream>>>(pt_tokens, pt_stride, n_prompt, ntok, B,
                                                                            Ncap, sos, tokens, tstride);
   count_launch(c); check_launch("build_inst_prompts");
+}
+void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo,
+                   const uint8_t* kpm, int nimg, int M, int Mpad, float* partial, int* counters, int nsplit,
+                   bf16* out_hi, bf16* out_lo) {
+  int kps = (M + nsplit - 1) / nsplit;
+  kps = (kps + 7) & ~7;
+  const size_t sm = static_cast<size_t>(kps) * sizeof(float);
+  ALM_REQUIRE(sm <= 160 * 1024, ALM_ERR_UNSUPPORTED, "cross_attn_q1: split too long for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    ALM_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  dim3 grid(nimg * 8, nsplit);
+  cross_attn_q1_kernel<<<grid, XQ_THREADS, sm, c->stream>>>(q, kc_hi, kc_lo, vt_hi, vt_lo, kpm, M, Mpad, kps, partial,
+                                                            counters, out_hi, out_lo);
+  count_launch(c); check_launch("cross_attn_q1");
+}
+int cross_attn_q1_splits(Ctx* c, int nimg, int M) {
+  int ns = (2 * c->num_sms + nimg * 8 - 1) / (nimg * 8);
+  ns = std::max(1, std::min(ns, 16));
+  while (ns > 1 && (M + ns - 1) / ns < 256) --ns;
+  return ns;
 }
 void add_i32(Ctx* c, int* p, int v) {
   add_i32_kernel<<<1, 1, 0, c->stream>>>(p, v);

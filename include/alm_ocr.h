@@ -78,6 +78,7 @@ ALM_API const char* alm_version(void);
 
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
+ *          "trace_gemm" (capacity; see alm_trace_read),
  *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
@@ -88,6 +89,10 @@ ALM_API long alm_launch_count(alm_ctx* ctx, int reset);
  * tensor-core GEMM launch is bracketed by CUDA events on the context stream.  alm_profile_read synchronises,
  * returns the summed kernel time (ms), the summed algorithmic FLOPs (2*M*N*K) and the launch count, and clears. */
 ALM_API int alm_profile_read(alm_ctx* ctx, double* gemm_ms, double* gemm_flops, long* gemm_launches);
+/* In-kernel GEMM timeline (measurement aid): after alm_set_option(ctx, "trace_gemm", capacity) CTA 0 of every
+ * tcgen05 GEMM stamps %globaltimer at entry and exit.  Records are 6 x u64: start ns, end ns, M, N, K,
+ * tiles*1000 + BLOCK_N.  Works inside graph replays.  Reading clears the buffer. */
+ALM_API int alm_trace_read(alm_ctx* ctx, unsigned long long* out, int max_records, int* n_records);
 /* Times `iters` back-to-back launches of one [M,K]x[N,K]^T GEMM (operands pre-split, resident) with CUDA events
  * on the context stream; ms_per_launch is the average kernel duration. */
 ALM_API int alm_bench_gemm(alm_ctx* ctx, int M, int N, int K, int iters, float* ms_per_launch);

@@ -272,7 +272,45 @@ def g_mgp():
         m.ctx.set_option('nsplit', 3)
 
 
-GROUPS = {'mgp': g_mgp, 'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
+def g_trace():
+    """In-kernel timeline of the GEMMs inside one bench step (B=16, N=64): durations by shape + gaps."""
+    import collections
+    import numpy as np
+    import torch
+    from advancedliteratemachinery_b200 import OmniParserB200, OmniVocab
+    from advancedliteratemachinery_b200 import synthetic as W
+    sd = W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0)
+    m = OmniParserB200(sd, OmniVocab(pt_seq_length=128))
+    img = torch.randn(16, 3, 1024, 1024, device='cuda')
+    for it in range(2):
+        m.encode(img, None); m.decode()
+    m.ctx.set_option('trace_gemm', 20000)
+    torch.cuda.synchronize(); t0 = time.time()
+    m.encode(img, None)
+    m.memory_shape(); rec_enc = m.ctx.trace_read()
+    t1 = time.time()
+    m.decode()
+    t2 = time.time()
+    rec = m.ctx.trace_read()
+    print(f'encode {1e3 * (t1 - t0):.1f} ms ({len(rec_enc)} gemms)  decode {1e3 * (t2 - t1):.1f} ms ({len(rec)} gemms)')
+    for name, r in (('encode', rec_enc), ('decode', rec)):
+        if len(r) < 2:
+            continue
+        r = r[np.argsort(r[:, 0])]
+        dur = (r[:, 1] - r[:, 0]).astype(np.float64) / 1e3
+        gap = (r[1:, 0] - r[:-1, 1]).astype(np.float64) / 1e3
+        span = (r[-1, 1] - r[0, 0]) / 1e6
+        print(f'[{name}] span {span:.2f} ms, sum(gemm) {dur.sum() / 1e3:.2f} ms, sum(gaps) {gap.sum() / 1e3:.2f} ms')
+        agg = collections.defaultdict(list)
+        for i in range(len(r)):
+            agg[(int(r[i, 2]), int(r[i, 3]), int(r[i, 4]), int(r[i, 5]))].append(dur[i])
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:28]:
+            print(f'   M={k[0]:8d} N={k[1]:6d} K={k[2]:5d} tiles={k[3] // 1000:6d} BN={k[3] % 1000:3d} n={len(v):5d} avg={np.mean(v):8.2f} us total={sum(v) / 1e3:8.2f} ms')
+        gs = np.sort(gap)
+        print(f'   gaps: median {np.median(gap):.2f} us  p90 {gs[int(0.9 * len(gs))]:.2f} us  max {gs[-1]:.1f} us')
+
+
+GROUPS = {'trace': g_trace, 'mgp': g_mgp, 'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
           'enc': g_enc, 'dec': g_dec, 'perf': g_perf}
 
 if __name__ == '__main__':
