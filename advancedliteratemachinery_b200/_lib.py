@@ -46,6 +46,8 @@ SIGNATURES = {
     'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
     'alm_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'alm_trace_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'alm_bench_gemm_ex': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_float), C.c_void_p]),
     'alm_bench_gemm': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     'alm_load_weights': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorDesc), C.c_int]),
     'alm_omni_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -114,6 +116,14 @@ class Context:
         n = C.c_int()
         self.check(self.lib.alm_trace_read(self.h, buf.ctypes.data, max_records, C.byref(n)))
         return buf[:n.value]
+
+    def bench_gemm_ex(self, M, N, K, batch=1, split_out=0, act=0, iters=10, detail=False):
+        import numpy as np
+        ms = C.c_float()
+        buf = np.zeros((64, 6), dtype=np.uint64)
+        self.check(self.lib.alm_bench_gemm_ex(self.h, M, N, K, batch, split_out, act, iters, C.byref(ms),
+                                              buf.ctypes.data if detail else None))
+        return ms.value, buf
 
     def bench_gemm(self, M, N, K, iters=20) -> float:
         ms = C.c_float()

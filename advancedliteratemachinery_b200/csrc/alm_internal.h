@@ -126,6 +126,8 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t stream2 = nullptr;  // second stream: the poly and rec decode loops overlap
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int num_sms = 148;
   std::string err;
   Arena ws;
@@ -136,10 +138,10 @@ struct Ctx {
   long launches = 0;  // kernels launched since last reset (gpu_launches in bench.py)
   // memoised TMA descriptors (see gemm.cu)
   struct TmapKey {
-    const void* base; int K, rows; long ld; int nb0, nb1; long bs0, bs1; int box_rows;
+    const void* base; int K, rows; long ld; int nb0, nb1; long bs0, bs1; int box_rows; long plane;
     bool operator==(const TmapKey& o) const {
       return base == o.base && K == o.K && rows == o.rows && ld == o.ld && nb0 == o.nb0 && nb1 == o.nb1 &&
-             bs0 == o.bs0 && bs1 == o.bs1 && box_rows == o.box_rows;
+             bs0 == o.bs0 && bs1 == o.bs1 && box_rows == o.box_rows && plane == o.plane;
     }
   };
   struct TmapHash {
@@ -147,7 +149,7 @@ struct Ctx {
       size_t h = reinterpret_cast<size_t>(k.base);
       auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
       mix(k.K); mix(k.rows); mix(static_cast<size_t>(k.ld)); mix(k.nb0); mix(k.nb1);
-      mix(static_cast<size_t>(k.bs0)); mix(static_cast<size_t>(k.bs1)); mix(k.box_rows);
+      mix(static_cast<size_t>(k.bs0)); mix(static_cast<size_t>(k.bs1)); mix(k.box_rows); mix(static_cast<size_t>(k.plane));
       return h;
     }
   };
@@ -156,6 +158,7 @@ struct Ctx {
   unsigned long long* trace_buf = nullptr;  // optional in-kernel GEMM timeline (alm_set_option "trace_gemm")
   int* trace_idx = nullptr;
   int trace_cap = 0;
+  unsigned long long* detail_buf = nullptr;  // [64][6] per-role stamps of CTA 0, overwritten by every GEMM (debug)
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;

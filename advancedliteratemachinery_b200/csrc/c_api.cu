@@ -143,6 +143,8 @@ void alm_free(alm_ctx* h) {
   if (h->c.ws.base) cudaFree(h->c.ws.base);
   if (h->dev_in) cudaFree(h->dev_in);
   if (h->dev_mask) cudaFree(h->dev_mask);
+  if (h->c.stream2) cudaStreamDestroy(h->c.stream2);
+  if (h->c.ev_fork) { cudaEventDestroy(h->c.ev_fork); cudaEventDestroy(h->c.ev_join); }
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
   delete h;
 }
@@ -165,6 +167,12 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
         ALM_CHECK_CUDA(cudaMalloc(&h->c.trace_buf, static_cast<size_t>(value) * 6 * sizeof(unsigned long long)));
         ALM_CHECK_CUDA(cudaMalloc(&h->c.trace_idx, sizeof(int)));
         ALM_CHECK_CUDA(cudaMemset(h->c.trace_idx, 0, sizeof(int)));
+      }
+    } else if (k == "trace_detail") {
+      if (h->c.detail_buf) { cudaFree(h->c.detail_buf); h->c.detail_buf = nullptr; }
+      if (value) {
+        ALM_CHECK_CUDA(cudaMalloc(&h->c.detail_buf, 64 * 6 * sizeof(unsigned long long)));
+        ALM_CHECK_CUDA(cudaMemset(h->c.detail_buf, 0, 64 * 6 * sizeof(unsigned long long)));
       }
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
@@ -217,6 +225,47 @@ int alm_trace_read(alm_ctx* h, unsigned long long* out, int max_records, int* n_
     ALM_CHECK_CUDA(cudaMemcpy(out, h->c.trace_buf, static_cast<size_t>(n) * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     ALM_CHECK_CUDA(cudaMemset(h->c.trace_idx, 0, sizeof(int)));
     *n_records = n;
+  });
+}
+
+int alm_bench_gemm_ex(alm_ctx* h, int M, int N, int K, int batch, int split_out, int act, int iters,
+                      float* ms_per_launch, unsigned long long* detail_out /* 64*6 or NULL */) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && batch > 0 && iters > 0 && ms_per_launch, ALM_ERR_INVALID,
+                "alm_bench_gemm_ex arguments");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    const size_t na = static_cast<size_t>(batch) * M * K, nb = static_cast<size_t>(batch) * N * K;
+    const int ldo = (N + 7) & ~7;
+    Operand a, b;
+    bf16* ah = c->ws.get<bf16>(na); bf16* al = c->ws.get<bf16>(na);
+    bf16* bh = c->ws.get<bf16>(nb); bf16* bl = c->ws.get<bf16>(nb);
+    ALM_CHECK_CUDA(cudaMemsetAsync(ah, 0x3c, na * 2, c->stream)); ALM_CHECK_CUDA(cudaMemsetAsync(al, 0x30, na * 2, c->stream));
+    ALM_CHECK_CUDA(cudaMemsetAsync(bh, 0x3c, nb * 2, c->stream)); ALM_CHECK_CUDA(cudaMemsetAsync(bl, 0x30, nb * 2, c->stream));
+    a.hi = ah; a.lo = al; a.rows = M; a.K = K; a.ld = K; a.nb0 = batch; a.bs0 = static_cast<long>(M) * K;
+    b.hi = bh; b.lo = bl; b.rows = N; b.K = K; b.ld = K; b.nb0 = batch; b.bs0 = static_cast<long>(N) * K;
+    Epilogue e;
+    const size_t no = static_cast<size_t>(batch) * M * ldo;
+    if (split_out) { e.out_hi = c->ws.get<bf16>(no); e.out_lo = c->ws.get<bf16>(no); }
+    else e.out_f32 = c->ws.get<float>(no);
+    e.ldo = ldo; e.obs0 = static_cast<long>(M) * ldo; e.act = act;
+    for (int i = 0; i < 3; ++i) gemm(c, a, b, e);
+    cudaEvent_t e0, e1;
+    ALM_CHECK_CUDA(cudaEventCreate(&e0));
+    ALM_CHECK_CUDA(cudaEventCreate(&e1));
+    ALM_CHECK_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; ++i) gemm(c, a, b, e);
+    ALM_CHECK_CUDA(cudaEventRecord(e1, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    ALM_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / iters;
+    if (detail_out && c->detail_buf)
+      ALM_CHECK_CUDA(cudaMemcpy(detail_out, c->detail_buf, 64 * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    c->ws.release(mk);
   });
 }
 

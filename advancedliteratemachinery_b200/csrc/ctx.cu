@@ -75,8 +75,11 @@ SplitW upload_split(Ctx* c, const float* w, int N, int K, int Kpad) {
     }
   SplitW s;
   s.N = N; s.K = Kpad; s.ld = Kpad;
-  s.hi = static_cast<bf16*>(c->walloc(hi.size() * 2));
-  s.lo = static_cast<bf16*>(c->walloc(lo.size() * 2));
+  // one allocation for both planes: the GEMM fetches hi and lo with a single 5-D TMA box, so lo must sit at a
+  // fixed positive distance after hi
+  const size_t plane = (hi.size() * 2 + 255) & ~size_t(255);
+  s.hi = static_cast<bf16*>(c->walloc(2 * plane));
+  s.lo = reinterpret_cast<bf16*>(reinterpret_cast<char*>(s.hi) + plane);
   ALM_CHECK_CUDA(cudaMemcpy(s.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
   ALM_CHECK_CUDA(cudaMemcpy(s.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
   return s;

@@ -26,7 +26,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreads = 352;  // warp 0 TMA(A), warp 1 MMA, warps 2..9 epilogue, warp 10 TMA(B)
 constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 16;
 
@@ -46,6 +46,7 @@ struct GemmParams {
   unsigned long long* trace;  // optional [cap][6] records: start ns, end ns (CTA 0), M, N, K, tiles
   int* trace_idx;
   int trace_cap;
+  unsigned long long* detail;  // optional [64 tiles][6] per-role timestamps of CTA 0 (debug)
 };
 
 template <int BLOCK_N, int NSPLIT>
@@ -73,6 +74,34 @@ __device__ __forceinline__ void split_pack_bf16x2(float x, float y, uint32_t& hi
   const float rx = x - __uint_as_float(hi << 16);
   const float ry = y - __uint_as_float(hi & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
+
+// Epilogue inner loop for one thread: 8 rows x 4 consecutive columns, everything already in registers.
+// Compile-time activation / output kinds keep this a short branch-free instruction stream (the epilogue warps
+// have one or two warps per scheduler, so instruction count is what bounds small-K GEMMs).
+template <int ACT, int F32, int SPLIT>
+__device__ __forceinline__ void epi_store8(const float4 (&acc)[8], const int (&orow)[8], const float (&rbias)[8],
+                                           const float4 (&res)[8], const float4& bb, float alpha, long ocol, long ldo,
+                                           float* __restrict__ out_f32, bf16* __restrict__ out_hi,
+                                           bf16* __restrict__ out_lo) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (orow[i] < 0) continue;
+    float f0 = fmaf(acc[i].x, alpha, rbias[i] + bb.x), f1 = fmaf(acc[i].y, alpha, rbias[i] + bb.y);
+    float f2 = fmaf(acc[i].z, alpha, rbias[i] + bb.z), f3 = fmaf(acc[i].w, alpha, rbias[i] + bb.w);
+    if (ACT == ACT_GELU) { f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3); }
+    if (ACT == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+    f0 += res[i].x; f1 += res[i].y; f2 += res[i].z; f3 += res[i].w;
+    const long o = ocol + static_cast<long>(orow[i]) * ldo;
+    if (F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(f0, f1, f2, f3);
+    if (SPLIT) {
+      uint32_t h01, l01, h23, l23;
+      split_pack_bf16x2(f0, f1, h01, l01);
+      split_pack_bf16x2(f2, f3, h23, l23);
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h01, h23);
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l01, l23);
+    }
+  }
 }
 
 template <int BLOCK_N, int NSPLIT>
@@ -106,12 +135,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
     ptx::prefetch_tmap(&tm_b_hi);
-    if (NSPLIT == 3) {
-      ptx::prefetch_tmap(&tm_a_lo);
-      ptx::prefetch_tmap(&tm_b_lo);
-    }
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp (A tiles, B tiles)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -128,9 +153,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   const long tiles_per_batch = static_cast<long>(p.m_blocks) * p.n_blocks;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+  if (warp == 0 || warp == 10) {
+    // ===================================================================== TMA producers
+    // Two single-thread producers in different warps (A tiles / B tiles): a lone thread issues one bulk-tensor
+    // copy every ~0.25 us, which bounds both the small-tile decode GEMMs and the big ones; two issue in parallel.
+    {
+      // the whole warp runs the (warp-uniform) loop and one elected lane issues: operands of UTMALDG / UTCHMMA live
+      // in uniform registers, and a `lane == 0` branch would make ptxas wrap every issue in an ELECT/R2UR loop
+      const bool is_a = (warp == 0);
+      const int my_bytes = is_a ? L::kNumA * p.a_bytes : L::kNumB * L::kBBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -138,26 +169,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const int rem = static_cast<int>(tile % tiles_per_batch);
         const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
         const int b0 = batch % p.nb0, b1 = batch / p.nb0;
-        const int a0 = p.a_b0 ? b0 : 0, a1 = p.a_b1 ? b1 : 0;
-        const int w0 = p.b_b0 ? b0 : 0, w1 = p.b_b1 ? b1 : 0;
+        const int c2 = is_a ? (p.a_b0 ? b0 : 0) : (p.b_b0 ? b0 : 0);
+        const int c3 = is_a ? (p.a_b1 ? b1 : 0) : (p.b_b1 ? b1 : 0);
+        const int rowc = is_a ? m_blk * BLOCK_M : n_blk * BLOCK_N;
+        const void* tm = is_a ? static_cast<const void*>(&tm_a_hi) : static_cast<const void*>(&tm_b_hi);
+        const long tl = (tile - blockIdx.x) / gridDim.x;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = stage_base + stage * p.stage_bytes;
-          ptx::mbar_expect_tx(&full_bar[stage], p.stage_tx);
-          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
-          if (NSPLIT == 3)
-            ptx::tma_load_4d(st + p.a_bytes, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M, a0, a1);
-          uint8_t* sb = st + L::kNumA * p.a_bytes;
-          ptx::tma_load_4d(sb, &tm_b_hi, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
-          if (NSPLIT == 3)
-            ptx::tma_load_4d(sb + L::kBBytes, &tm_b_lo, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N, w0, w1);
+          if (p.detail && is_a && blockIdx.x == 0 && tl < 64 && kb == 0 && lane == 0) p.detail[tl * 6 + 0] = ptx::globaltimer_ns();
+          uint8_t* dst = stage_base + stage * p.stage_bytes + (is_a ? 0 : L::kNumA * p.a_bytes);
+          if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
+          if (NSPLIT == 3) {
+            // hi and lo planes of an operand sit at a fixed distance in HBM: ONE 5-D box {k, rows, plane = 2}
+            // fetches both tiles back to back
+            ptx::tma_load_5d(dst, tm, &full_bar[stage], kb * BLOCK_K, rowc, 0, c2, c3);
+          } else {
+            ptx::tma_load_4d(dst, tm, &full_bar[stage], kb * BLOCK_K, rowc, c2, c3);
+          }
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
                                  (uint32_t(BLOCK_M >> 4) << 24);
@@ -166,16 +204,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       int as = 0;
       uint32_t aphase = 0;
       for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const long tl = (tile - blockIdx.x) / gridDim.x;
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
+        if (p.detail && blockIdx.x == 0 && tl < 64 && lane == 0) p.detail[tl * 6 + 1] = ptx::globaltimer_ns();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          if (p.detail && blockIdx.x == 0 && tl < 64 && kb == 0 && lane == 0) p.detail[tl * 6 + 2] = ptx::globaltimer_ns();
           const uint32_t a_hi = ptx::smem_u32(stage_base + stage * p.stage_bytes);
           const uint32_t a_lo = a_hi + p.a_bytes;
           const uint32_t b_hi = a_hi + L::kNumA * p.a_bytes;
           const uint32_t b_lo = b_hi + L::kBBytes;
+          if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128 B swizzle row
@@ -190,9 +232,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (p.detail && blockIdx.x == 0 && tl < 64 && lane == 0) p.detail[tl * 6 + 3] = ptx::globaltimer_ns();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -213,8 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int rem = static_cast<int>(tile % tiles_per_batch);
       const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
       const int b0 = batch % p.nb0, b1 = batch / p.nb0;
+      const long tl = (tile - blockIdx.x) / gridDim.x;
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
+      if (p.detail && blockIdx.x == 0 && tl < 64 && warp == 4 && lane == 0) p.detail[tl * 6 + 4] = ptx::globaltimer_ns();
       const long obatch = static_cast<long>(b0) * e.obs0 + static_cast<long>(b1) * e.obs1;
       const float* rbatch = e.resid ? e.resid + static_cast<long>(b0) * e.rbs0 + static_cast<long>(b1) * e.rbs1 : nullptr;
       const float* bias = e.bias ? e.bias + static_cast<long>(b0) * e.bias_bs0 : nullptr;
@@ -237,9 +285,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const bool col_ok = col < p.N;
         const bool vec = p.vec_ok && col + 3 < p.N;
         // phase 1: everything this thread needs for its 8 rows is requested up front (independent loads in
-        // flight: staging reads, row maps, residual lines) -- the epilogue is latency-bound otherwise.
+        // flight: staging reads, row maps, row biases, residual lines) -- the epilogue is latency-bound otherwise.
         float4 acc[8];
         int orow[8], rrow[8];
+        float rbias[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rl_base;
@@ -249,51 +298,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           if (o >= 0 && e.out_map) o = e.out_map[row];
           orow[i] = o;
           rrow[i] = (o >= 0 && e.resid_map) ? e.resid_map[row] : o;
+          rbias[i] = (o >= 0 && bias && e.bias_mode == BIAS_ROW) ? bias[row] : 0.0f;
         }
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec && bias && e.bias_mode == BIAS_COL) bb = *reinterpret_cast<const float4*>(bias + col);
-        float4 res[8];
-        if (rbatch && vec) {
+        if (vec) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && e.bias_mode == BIAS_COL) bb = *reinterpret_cast<const float4*>(bias + col);
+          float4 res[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            res[i] = rrow[i] >= 0 ? *reinterpret_cast<const float4*>(rbatch + static_cast<long>(rrow[i]) * e.ldr + col)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // phase 2: math + stores
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (orow[i] < 0) continue;
-          const int row = row_base + i * 4 + rl_base;
-          const long o = obatch + static_cast<long>(orow[i]) * e.ldo + col;
-          float f[4] = {acc[i].x * e.alpha, acc[i].y * e.alpha, acc[i].z * e.alpha, acc[i].w * e.alpha};
-          if (bias && e.bias_mode == BIAS_ROW) {
-            const float rb = bias[row];
-            f[0] += rb; f[1] += rb; f[2] += rb; f[3] += rb;
+            res[i] = (rbatch && rrow[i] >= 0)
+                         ? *reinterpret_cast<const float4*>(rbatch + static_cast<long>(rrow[i]) * e.ldr + col)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          // phase 2: straight-line math + stores; the option checks are hoisted into one switch per chunk
+          const int kind = e.act * 4 + (e.out_f32 ? 1 : 0) + (e.out_hi ? 2 : 0);
+          const long ocol = obatch + col;
+          switch (kind) {
+#define ALM_EPI_CASE(ACTV, F32V, SPLV)                                                                         \
+  case (ACTV) * 4 + (F32V) + 2 * (SPLV):                                                                        \
+    epi_store8<ACTV, F32V, SPLV>(acc, orow, rbias, res, bb, e.alpha, ocol, e.ldo, e.out_f32, e.out_hi, e.out_lo); \
+    break;
+            ALM_EPI_CASE(0, 1, 0) ALM_EPI_CASE(0, 0, 1) ALM_EPI_CASE(0, 1, 1)
+            ALM_EPI_CASE(1, 1, 0) ALM_EPI_CASE(1, 0, 1) ALM_EPI_CASE(1, 1, 1)
+            ALM_EPI_CASE(2, 1, 0) ALM_EPI_CASE(2, 0, 1) ALM_EPI_CASE(2, 1, 1)
+#undef ALM_EPI_CASE
+            default: break;
           }
-          if (vec) {
-            f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
-            if (e.act == ACT_GELU) {
+        } else {
+          // ragged / unaligned tail: scalar, guarded (fully unrolled so the row arrays stay in registers)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) f[q] = gelu_erf(f[q]);
-            } else if (e.act == ACT_RELU) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.0f);
-            }
-            if (rbatch) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
-            if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(f[0], f[1], f[2], f[3]);
-            if (e.out_hi) {
-              uint32_t h01, l01, h23, l23;
-              split_pack_bf16x2(f[0], f[1], h01, l01);
-              split_pack_bf16x2(f[2], f[3], h23, l23);
-              *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(h01, h23);
-              if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(l01, l23);
-            }
-          } else {
-            // ragged / unaligned tail: scalar, guarded
+          for (int i = 0; i < 8; ++i) {
+            if (orow[i] < 0) continue;
+            const long o = obatch + static_cast<long>(orow[i]) * e.ldo + col;
+            const float f[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col + q >= p.N) break;
-              float x = f[q];
+              float x = f[q] * e.alpha + rbias[i];
               if (bias && e.bias_mode == BIAS_COL) x += bias[col + q];
               if (e.act == ACT_GELU) x = gelu_erf(x);
               else if (e.act == ACT_RELU) x = fmaxf(x, 0.0f);
@@ -314,6 +354,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (p.detail && blockIdx.x == 0 && tl < 64 && warp == 4 && lane == 0) p.detail[tl * 6 + 5] = ptx::globaltimer_ns();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -391,8 +432,8 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
 
 // Encoding a descriptor is a driver call (a few microseconds); the decode loop re-issues the same few hundred
 // (pointer, geometry) pairs every token, so descriptors are memoised per context.
-const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows) {
-  Ctx::TmapKey key{base, op.K, op.rows, op.ld, op.nb0, op.nb1, op.bs0, op.bs1, box_rows};
+const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int box_rows, long plane_stride) {
+  Ctx::TmapKey key{base, op.K, op.rows, op.ld, op.nb0, op.nb1, op.bs0, op.bs1, box_rows, plane_stride};
   auto it = c->tmap_cache.find(key);
   if (it != c->tmap_cache.end()) return it->second;
   if (c->tmap_cache.size() > 20000) c->tmap_cache.clear();
@@ -401,18 +442,31 @@ const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int bo
   ALM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, ALM_ERR_INVALID, "gemm operand not 16-byte aligned");
   ALM_REQUIRE(op.ld % 8 == 0 && op.bs0 % 8 == 0 && op.bs1 % 8 == 0, ALM_ERR_INVALID,
               "gemm operand strides must be multiples of 8 elements");
-  cuuint64_t dims[4] = {cuuint64_t(op.K), cuuint64_t(op.rows), cuuint64_t(op.nb0), cuuint64_t(op.nb1)};
   const cuuint64_t row_bytes = cuuint64_t(op.ld) * 2;
   cuuint64_t s1 = op.nb0 > 1 ? cuuint64_t(op.bs0) * 2 : row_bytes * cuuint64_t(op.rows);
   cuuint64_t s2 = op.nb1 > 1 ? cuuint64_t(op.bs1) * 2 : s1 * cuuint64_t(op.nb0);
   if (s1 == 0) s1 = row_bytes;  // degenerate broadcast dims still need a legal stride
   if (s2 == 0) s2 = s1;
-  cuuint64_t strides[3] = {row_bytes, s1, s2};
-  cuuint32_t box[4] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (plane_stride > 0) {
+    // 5-D: {k, row, plane(hi, lo), batch0, batch1}
+    ALM_REQUIRE(plane_stride % 8 == 0, ALM_ERR_INVALID, "hi/lo planes must be a multiple of 16 bytes apart");
+    cuuint64_t dims[5] = {cuuint64_t(op.K), cuuint64_t(op.rows), 2, cuuint64_t(op.nb0), cuuint64_t(op.nb1)};
+    cuuint64_t strides[4] = {row_bytes, cuuint64_t(plane_stride) * 2, s1, s2};
+    cuuint32_t box[5] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 2, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[4] = {cuuint64_t(op.K), cuuint64_t(op.rows), cuuint64_t(op.nb0), cuuint64_t(op.nb1)};
+    cuuint64_t strides[3] = {row_bytes, s1, s2};
+    cuuint32_t box[4] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS)
     throw AlmError{ALM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)) +
                                      " (K=" + std::to_string(op.K) + " rows=" + std::to_string(op.rows) +
@@ -438,10 +492,16 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   p.stage_bytes = L::kNumA * p.a_bytes + L::kNumB * L::kBBytes;
   p.stage_tx = p.stage_bytes;
   p.stages = std::min(kMaxStages, L::kBudget / p.stage_bytes);
-  const CUtensorMap ta_hi = make_tmap(c, A.hi, A, a_rows);  // by value: the cache may be cleared by a later call
-  const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N);
-  const CUtensorMap ta_lo = (NSPLIT == 3) ? make_tmap(c, A.lo, A, a_rows) : ta_hi;
-  const CUtensorMap tb_lo = (NSPLIT == 3) ? make_tmap(c, B.lo, B, BLOCK_N) : tb_hi;
+  // by value: the descriptor cache may be cleared by a later call
+  long pa = 0, pb = 0;
+  if (NSPLIT == 3) {
+    pa = A.lo - A.hi;
+    pb = B.lo - B.hi;
+    ALM_REQUIRE(pa > 0 && pb > 0, ALM_ERR_INVALID, "split operands must be allocated hi plane first, lo plane after");
+  }
+  const CUtensorMap ta_hi = make_tmap(c, A.hi, A, a_rows, pa);
+  const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N, pb);
+  const CUtensorMap ta_lo = ta_hi, tb_lo = tb_hi;  // kept in the signature; the 5-D maps cover both planes
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, c->num_sms));
   kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
@@ -473,6 +533,7 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
   if (E.bias && E.bias_mode == BIAS_COL) vec = vec && (reinterpret_cast<uintptr_t>(E.bias) % 16 == 0) && (E.bias_bs0 % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
   p.trace = c->trace_buf; p.trace_idx = c->trace_idx; p.trace_cap = c->trace_cap;
+  p.detail = c->detail_buf;
   const int nsplit = c->nsplit;
   ALM_REQUIRE(nsplit == 1 || (A.lo && B.lo), ALM_ERR_INVALID, "gemm: split mode needs lo operands");
 

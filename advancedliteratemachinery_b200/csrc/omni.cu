@@ -611,35 +611,62 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
   if (Ncap == 0) return;
 
   // ------------------------------------------------------------------ poly / rec loops (:249-284)
+  // The two loops only depend on the decoded points, not on each other: they run concurrently on two streams
+  // (their per-token kernels are far too small to fill 148 SMs one at a time).
+  if (!c->stream2) ALM_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  if (!c->ev_fork) {
+    ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t s0 = c->stream, s1 = c->stream2;
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_fork, s0));
+  ALM_CHECK_CUDA(cudaStreamWaitEvent(s1, c->ev_fork, 0));
+  ws.release(after_pt_tokens);
+  const int S = B * Ncap;
+  int* toks[3] = {nullptr, nullptr, nullptr};
+  float* prbs[3] = {nullptr, nullptr, nullptr};
+  try {
+    for (int phase = 1; phase <= 2; ++phase) {
+      c->stream = (phase == 1) ? s0 : s1;
+      const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
+      const int T = 3 + len;
+      int* tok = ws.get<int>(static_cast<size_t>(S) * T);
+      float* probs = ws.get<float>(static_cast<size_t>(S) * len);
+      toks[phase] = tok; prbs[phase] = probs;
+      fill_i32(c, tok, static_cast<long>(S) * T, 0);
+      build_inst_prompts(c, pt_tok, Tpt, n_prompt, ntok, B, Ncap, phase == 1 ? cfg.poly_sos : cfg.rec_sos, tok, T);
+      DecodeBufs u = alloc_decode(c, m, B, Ncap, T - 1);
+      fill_i32(c, u.tpos, 1, 0);
+      HeadArgs off;
+      run_steps(c, m, phase, u, tok, T, 0, B, 2, off);
+      HeadArgs h;
+      h.on = true; h.cfg = hc; h.tokens = tok; h.tstride = T; h.n_prompt_m1 = 2; h.probs = probs; h.pstride = len;
+      h.seqs_per_image = Ncap;
+      run_steps(c, m, phase, u, tok, T, 0, B, len, h);
+    }
+  } catch (...) {
+    c->stream = s0;
+    cudaStreamSynchronize(s1);
+    throw;
+  }
+  c->stream = s0;
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_join, s1));
+  ALM_CHECK_CUDA(cudaStreamWaitEvent(s0, c->ev_join, 0));
   for (int phase = 1; phase <= 2; ++phase) {
-    ws.release(after_pt_tokens);
     const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
     const int T = 3 + len;
-    const int S = B * Ncap;
-    int* tok = ws.get<int>(static_cast<size_t>(S) * T);
-    float* probs = ws.get<float>(static_cast<size_t>(S) * len);
-    fill_i32(c, tok, static_cast<long>(S) * T, 0);
-    build_inst_prompts(c, pt_tok, Tpt, n_prompt, ntok, B, Ncap, phase == 1 ? cfg.poly_sos : cfg.rec_sos, tok, T);
-    DecodeBufs u = alloc_decode(c, m, B, Ncap, T - 1);
-    fill_i32(c, u.tpos, 1, 0);
-    HeadArgs off;
-    run_steps(c, m, phase, u, tok, T, 0, B, 2, off);
-    HeadArgs h;
-    h.on = true; h.cfg = hc; h.tokens = tok; h.tstride = T; h.n_prompt_m1 = 2; h.probs = probs; h.pstride = len;
-    h.seqs_per_image = Ncap;
-    run_steps(c, m, phase, u, tok, T, 0, B, len, h);
     std::vector<int> hh(static_cast<size_t>(S) * T);
     std::vector<float> hp(static_cast<size_t>(S) * len);
-    ALM_CHECK_CUDA(cudaMemcpyAsync(hh.data(), tok, hh.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    ALM_CHECK_CUDA(cudaMemcpyAsync(hp.data(), probs, hp.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaMemcpyAsync(hh.data(), toks[phase], hh.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ALM_CHECK_CUDA(cudaMemcpyAsync(hp.data(), prbs[phase], hp.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
     for (int b = 0; b < B; ++b)
       for (int n = 0; n < n_inst[b]; ++n) {
-        const size_t s = static_cast<size_t>(b) * Ncap + n;
+        const size_t sq = static_cast<size_t>(b) * Ncap + n;
         for (int k = 0; k < len; ++k) {
           const size_t o = (static_cast<size_t>(b) * maxI + n) * len + k;
-          if (phase == 1) poly[o] = hh[s * T + 3 + k];
-          else { rec[o] = hh[s * T + 3 + k]; rec_prob[o] = hp[s * len + k]; }
+          if (phase == 1) poly[o] = hh[sq * T + 3 + k];
+          else { rec[o] = hh[sq * T + 3 + k]; rec_prob[o] = hp[sq * len + k]; }
         }
       }
   }

@@ -78,7 +78,7 @@ ALM_API const char* alm_version(void);
 
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
- *          "trace_gemm" (capacity; see alm_trace_read),
+ *          "trace_gemm" (capacity; see alm_trace_read), "trace_detail" (see alm_bench_gemm_ex),
  *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
@@ -96,6 +96,11 @@ ALM_API int alm_trace_read(alm_ctx* ctx, unsigned long long* out, int max_record
 /* Times `iters` back-to-back launches of one [M,K]x[N,K]^T GEMM (operands pre-split, resident) with CUDA events
  * on the context stream; ms_per_launch is the average kernel duration. */
 ALM_API int alm_bench_gemm(alm_ctx* ctx, int M, int N, int K, int iters, float* ms_per_launch);
+/* Same, batched, with a choice of epilogue (split_out: bf16 hi/lo output; act: 0/1/2).  With the "trace_detail" option
+ * on, detail_out receives 64 x 6 u64 stamps of CTA 0's first tiles: TMA issue, MMA tile start, operands landed,
+ * MMA committed, epilogue start, epilogue end (ns, %globaltimer). */
+ALM_API int alm_bench_gemm_ex(alm_ctx* ctx, int M, int N, int K, int batch, int split_out, int act, int iters,
+                              float* ms_per_launch, unsigned long long* detail_out);
 
 /* Replaces reference `model.load_state_dict(torch.load(path)['model'])`
  * (OCR/OmniParser/utils/checkpointer.py:44-47; OCR/MGP-STR/test_final.py:353-356). */

@@ -310,7 +310,27 @@ def g_trace():
         print(f'   gaps: median {np.median(gap):.2f} us  p90 {gs[int(0.9 * len(gs))]:.2f} us  max {gs[-1]:.1f} us')
 
 
-GROUPS = {'trace': g_trace, 'mgp': g_mgp, 'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
+def g_detail():
+    """Per-role timeline of CTA 0 for a few GEMM shapes (where does a tile's time go?)."""
+    import numpy as np
+    c = _ctx()
+    c.set_option('trace_detail', 1)
+    for (M, N, K, batch, split, act, tag) in [(64, 4096, 64, 128, 0, 0, 'decode scores'), (16, 512, 512, 1, 0, 0, 'pt linear'),
+                                              (16, 512, 2048, 1, 0, 0, 'pt ffn2'), (65536, 2048, 512, 1, 1, 1, 'stage2 fc1 gelu split'),
+                                              (65536, 512, 2048, 1, 0, 0, 'stage2 fc2'), (1048576, 128, 128, 1, 0, 0, 'stage0 proj-like'),
+                                              (1048576, 512, 128, 1, 1, 1, 'stage0 fc1')]:
+        ms, d = c.bench_gemm_ex(M, N, K, batch, split, act, iters=5, detail=True)
+        d = d.astype(np.int64)
+        t0 = d[0, 0]
+        print(f'--- {tag}: M={M} N={N} K={K} batch={batch} split={split} act={act}: {ms * 1e3:.1f} us/launch')
+        print('   tile:  tma_issue  mma_start  operands   committed  epi_start  epi_end   (us since first TMA issue)')
+        for t in range(8):
+            if d[t, 0] == 0:
+                break
+            print('   %3d: ' % t + ' '.join('%9.2f' % ((d[t, j] - t0) / 1e3) for j in range(6)))
+
+
+GROUPS = {'detail': g_detail, 'trace': g_trace, 'mgp': g_mgp, 'simt': g_simt, 'tc': g_tc, 'tcbig': g_tcbig, 'ln': g_ln, 'wattn': g_wattn, 'enc_simt': g_enc_simt,
           'enc': g_enc, 'dec': g_dec, 'perf': g_perf}
 
 if __name__ == '__main__':
