@@ -56,6 +56,8 @@ SIGNATURES = {
     'alm_omni_memory_shape': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'alm_omni_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    'alm_omni_decode_kie': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'alm_omni_decode_logits': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'alm_omni_vocab': (C.c_int, [C.c_void_p]),
     'alm_mgpstr_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -397,6 +397,16 @@ int alm_omni_decode(alm_ctx* h, const int64_t* pt_prompt, int n_prompt, const al
   });
 }
 
+int alm_omni_decode_kie(alm_ctx* h, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_tok,
+                        int64_t* pt_tokens, float* pt_probs, int32_t* n_inst, int32_t* inst_pos, int64_t* poly,
+                        int64_t* rec, float* rec_prob) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(pt_prompt && cfg && n_tok && pt_tokens && pt_probs && n_inst && inst_pos && poly && rec && rec_prob,
+                ALM_ERR_INVALID, "null argument");
+    omni_decode_kie(&h->c, pt_prompt, n_prompt, *cfg, n_tok, pt_tokens, pt_probs, n_inst, inst_pos, poly, rec, rec_prob);
+  });
+}
+
 int alm_omni_decode_logits(alm_ctx* h, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
   return guarded(h, [&] {
     ALM_REQUIRE(seq && logits, ALM_ERR_INVALID, "null argument");

@@ -485,6 +485,7 @@ struct HeadArgs {
   int* finished = nullptr;
   int* ntok = nullptr;
   int seqs_per_image = 1;
+  int nsoft = 0;  // logits entering the softmax (V, or V - vie_categories for the KIE poly/rec loops)
 };
 
 // `n` consecutive token steps of decoder d.  The step (all ~62 launches + the counter increment) is captured once
@@ -496,7 +497,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
   auto body = [&] {
     decoder_step(c, m, d, u, tokens, tstride, img0, nimg, h.on);
     if (h.on)
-      head_select(c, u.logits, u.S, m->V, m->V, d, h.cfg, h.tokens, h.tstride, u.tpos, h.n_prompt_m1, h.probs, h.pstride,
+      head_select(c, u.logits, u.S, m->V, h.nsoft ? h.nsoft : m->V, d, h.cfg, h.tokens, h.tstride, u.tpos, h.n_prompt_m1, h.probs, h.pstride,
                   h.finished, h.ntok, h.seqs_per_image);
     add_i32(c, u.tpos, 1);
   };
@@ -508,7 +509,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf)};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {
@@ -539,24 +540,30 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
 
 }  // namespace
 
-void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
-                 int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
+// Greedy decoding of every encoded image.  Text spotting (transformer.py:234-286) and KIE (:143-217) share the
+// pt loop and the batched poly / rec loops; they differ in the pt step pattern (x, y[, class]), in which decoded
+// tokens form (x, y) instances and in the number of logits entering the poly / rec softmax.
+void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, bool kie,
+                      int32_t* n_tok_out, int64_t* pt_tok_out, float* pt_prob_out, int32_t* n_inst, int32_t* inst_pos,
+                      int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode before alm_omni_encode");
   ALM_REQUIRE(n_prompt >= 1 && n_prompt <= 16, ALM_ERR_INVALID, "pt prompt length");
   ALM_REQUIRE(cfg.pt_seq_length >= 1 && n_prompt + cfg.pt_seq_length - 1 <= 1024, ALM_ERR_INVALID,
               "prompt + pt_seq_length exceeds the 1024-row position table (transformer.py:475)");
-  ALM_REQUIRE(cfg.vie_categories == 0 && m->vie == 0, ALM_ERR_UNSUPPORTED, "KIE decode is not built yet (SURVEY 8f-3)");
+  ALM_REQUIRE(cfg.vie_categories == m->vie, ALM_ERR_INVALID, "vie_categories does not match the loaded checkpoint");
+  ALM_REQUIRE(kie == (m->vie > 0), ALM_ERR_INVALID, "use alm_omni_decode for text spotting and alm_omni_decode_kie for KIE");
   ALM_REQUIRE(cfg.max_instances >= (cfg.pt_seq_length / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
   ALM_REQUIRE(cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
   const int B = m->B;
   Arena& ws = c->ws;
   ws.release(m->ws_mark);
-  HeadCfg hc{cfg.num_bins, cfg.pt_eos, cfg.rec_eos, cfg.recog_pad, 0};
+  HeadCfg hc{cfg.num_bins, cfg.pt_eos, cfg.rec_eos, cfg.recog_pad, m->vie};
 
   // ------------------------------------------------------------------ pt loop (transformer.py:102-141)
   const int Tpt = n_prompt + cfg.pt_seq_length;
   int* pt_tok = ws.get<int>(static_cast<size_t>(B) * Tpt);
+  float* pt_prob = ws.get<float>(static_cast<size_t>(B) * cfg.pt_seq_length);
   int* finished = ws.get<int>(B);
   int* ntok = ws.get<int>(B);
   {
@@ -576,6 +583,7 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
     run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, n_prompt - 1, off);  // prompt tokens only fill the caches
     HeadArgs h;
     h.on = true; h.cfg = hc; h.tokens = pt_tok; h.tstride = Tpt; h.n_prompt_m1 = n_prompt - 1;
+    h.probs = pt_prob; h.pstride = cfg.pt_seq_length;
     h.finished = finished; h.ntok = ntok; h.seqs_per_image = 1;
     std::vector<int> fin(B);
     for (int done = 0; done < cfg.pt_seq_length;) {
@@ -589,28 +597,47 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
       }
     }
   }
-  std::vector<int> h_ntok(B);
+  std::vector<int> h_ntok(B), h_tok(static_cast<size_t>(B) * Tpt);
+  std::vector<float> h_prob(static_cast<size_t>(B) * cfg.pt_seq_length);
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_ntok.data(), ntok, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  ALM_CHECK_CUDA(cudaMemcpyAsync(h_tok.data(), pt_tok, h_tok.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  ALM_CHECK_CUDA(cudaMemcpyAsync(h_prob.data(), pt_prob, h_prob.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  const int maxI = cfg.max_instances;
+  // which decoded tokens form (x, y) instances
+  std::vector<std::vector<int>> starts(B);
   int Ncap = 0;
   for (int b = 0; b < B; ++b) {
-    n_inst[b] = h_ntok[b] / 2;
-    Ncap = std::max(Ncap, h_ntok[b] / 2);
-  }
-  ALM_REQUIRE(Ncap <= cfg.max_instances, ALM_ERR_INVALID, "decoded more points than max_instances");
-  const int maxI = cfg.max_instances;
-  {  // pt output: [B, max_inst, 2]
-    std::vector<int> h(static_cast<size_t>(B) * Tpt);
-    ALM_CHECK_CUDA(cudaMemcpyAsync(h.data(), pt_tok, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-    for (int b = 0; b < B; ++b)
-      for (int n = 0; n < n_inst[b]; ++n)
-        for (int k = 0; k < 2; ++k)
-          pt[(static_cast<size_t>(b) * maxI + n) * 2 + k] = h[static_cast<size_t>(b) * Tpt + n_prompt + 2 * n + k];
+    int len = h_ntok[b];
+    if (len % 2) --len;  // transformer.py:138-139 (applied in both modes by the reference)
+    const int* t = &h_tok[static_cast<size_t>(b) * Tpt + n_prompt];
+    if (!kie) {
+      for (int i = 0; i + 1 < len; i += 2) starts[b].push_back(i);
+    } else {
+      for (int i = 0; i < len;) {  // the walk of decode_vie_pt_poly_rec_seq (transformer.py:148-215)
+        if (t[i] < cfg.num_bins && i + 1 <= len - 1 && t[i + 1] < cfg.num_bins) { starts[b].push_back(i); i += 2; }
+        else ++i;
+      }
+      if (n_tok_out) n_tok_out[b] = len;
+      for (int i = 0; i < len; ++i) {
+        pt_tok_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = t[i];
+        pt_prob_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = h_prob[static_cast<size_t>(b) * cfg.pt_seq_length + i];
+      }
+    }
+    n_inst[b] = static_cast<int>(starts[b].size());
+    ALM_REQUIRE(n_inst[b] <= maxI, ALM_ERR_INVALID, "decoded more points than max_instances");
+    Ncap = std::max(Ncap, n_inst[b]);
+    for (int n = 0; n < n_inst[b]; ++n) {
+      if (inst_pos) inst_pos[static_cast<size_t>(b) * maxI + n] = starts[b][n];
+      if (pt) {
+        pt[(static_cast<size_t>(b) * maxI + n) * 2] = t[starts[b][n]];
+        pt[(static_cast<size_t>(b) * maxI + n) * 2 + 1] = t[starts[b][n] + 1];
+      }
+    }
   }
   if (Ncap == 0) return;
 
-  // ------------------------------------------------------------------ poly / rec loops (:249-284)
+  // ------------------------------------------------------------------ poly / rec loops (:249-284 ; :153-185 for KIE)
   // The two loops only depend on the decoded points, not on each other: they run concurrently on two streams
   // (their per-token kernels are far too small to fill 148 SMs one at a time).
   if (!c->stream2) ALM_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -619,30 +646,44 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
     ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
   cudaStream_t s0 = c->stream, s1 = c->stream2;
-  ALM_CHECK_CUDA(cudaEventRecord(c->ev_fork, s0));
-  ALM_CHECK_CUDA(cudaStreamWaitEvent(s1, c->ev_fork, 0));
   ws.release(after_pt_tokens);
   const int S = B * Ncap;
   int* toks[3] = {nullptr, nullptr, nullptr};
   float* prbs[3] = {nullptr, nullptr, nullptr};
+  std::vector<int> h_prompt[3];
+  for (int phase = 1; phase <= 2; ++phase) {  // [x, y, sos] per instance (transformer.py:252,268 ; :153,172); dead slots 0,0,sos
+    const int T = 3 + (phase == 1 ? cfg.poly_length : cfg.rec_length);
+    h_prompt[phase].assign(static_cast<size_t>(S) * T, 0);
+    for (int b = 0; b < B; ++b)
+      for (int n = 0; n < Ncap; ++n) {
+        int* row = &h_prompt[phase][(static_cast<size_t>(b) * Ncap + n) * T];
+        if (n < n_inst[b]) {
+          const int* t = &h_tok[static_cast<size_t>(b) * Tpt + n_prompt + starts[b][n]];
+          row[0] = t[0]; row[1] = t[1];
+        }
+        row[2] = phase == 1 ? cfg.poly_sos : cfg.rec_sos;
+      }
+    toks[phase] = ws.get<int>(static_cast<size_t>(S) * T);
+    prbs[phase] = ws.get<float>(static_cast<size_t>(S) * (T - 3));
+    ALM_CHECK_CUDA(cudaMemcpyAsync(toks[phase], h_prompt[phase].data(), h_prompt[phase].size() * sizeof(int),
+                                   cudaMemcpyHostToDevice, s0));
+  }
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_fork, s0));
+  ALM_CHECK_CUDA(cudaStreamWaitEvent(s1, c->ev_fork, 0));
   try {
     for (int phase = 1; phase <= 2; ++phase) {
       c->stream = (phase == 1) ? s0 : s1;
       const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
       const int T = 3 + len;
-      int* tok = ws.get<int>(static_cast<size_t>(S) * T);
-      float* probs = ws.get<float>(static_cast<size_t>(S) * len);
-      toks[phase] = tok; prbs[phase] = probs;
-      fill_i32(c, tok, static_cast<long>(S) * T, 0);
-      build_inst_prompts(c, pt_tok, Tpt, n_prompt, ntok, B, Ncap, phase == 1 ? cfg.poly_sos : cfg.rec_sos, tok, T);
       DecodeBufs u = alloc_decode(c, m, B, Ncap, T - 1);
       fill_i32(c, u.tpos, 1, 0);
       HeadArgs off;
-      run_steps(c, m, phase, u, tok, T, 0, B, 2, off);
+      run_steps(c, m, phase, u, toks[phase], T, 0, B, 2, off);
       HeadArgs h;
-      h.on = true; h.cfg = hc; h.tokens = tok; h.tstride = T; h.n_prompt_m1 = 2; h.probs = probs; h.pstride = len;
-      h.seqs_per_image = Ncap;
-      run_steps(c, m, phase, u, tok, T, 0, B, len, h);
+      h.on = true; h.cfg = hc; h.tokens = toks[phase]; h.tstride = T; h.n_prompt_m1 = 2; h.probs = prbs[phase];
+      h.pstride = len; h.seqs_per_image = Ncap;
+      h.nsoft = m->V - m->vie;  // logits[:, -1, :-vie_categories] (transformer.py:156,176)
+      run_steps(c, m, phase, u, toks[phase], T, 0, B, len, h);
     }
   } catch (...) {
     c->stream = s0;
@@ -671,6 +712,18 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
       }
   }
   ws.release(m->ws_mark);
+}
+
+void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
+                 int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
+  omni_decode_impl(c, pt_prompt, n_prompt, cfg, false, nullptr, nullptr, nullptr, n_inst, nullptr, pt, poly, rec, rec_prob);
+}
+
+void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_tok,
+                     int64_t* pt_tokens, float* pt_probs, int32_t* n_inst, int32_t* inst_pos, int64_t* poly,
+                     int64_t* rec, float* rec_prob) {
+  omni_decode_impl(c, pt_prompt, n_prompt, cfg, true, n_tok, pt_tokens, pt_probs, n_inst, inst_pos, nullptr, poly, rec,
+                   rec_prob);
 }
 
 // Teacher-forced logits for one image: every position of every sequence (Transformer.decode, :74-100).

@@ -81,6 +81,9 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t);
 void omni_encode(Ctx* c, const float* img_dev, const uint8_t* mask_dev, int B, int H, int W);
 void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
                  int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);
+void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_tok,
+                     int64_t* pt_tokens, float* pt_probs, int32_t* n_inst, int32_t* inst_pos, int64_t* poly,
+                     int64_t* rec, float* rec_prob);
 void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits);
 
 // kernels (omni_kernels.cu)

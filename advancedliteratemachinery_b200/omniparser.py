@@ -21,6 +21,17 @@ from .nested_tensor import NestedTensor
 DEFAULT_CHARS = ' !"#$%&\'()*+,-./0123456789:;<=>?@ABCDEFGHIJKLMNOPQRSTUVWXYZ[\\]^_`abcdefghijklmnopqrstuvwxyz{|}~'
 
 
+# entity classes of the two KIE datasets the reference supports (model/transformer.py:49-61); class id =
+# padding_index + 1 + position
+CLASSES_CORD = ['menu.cnt', 'menu.discountprice', 'menu.etc', 'menu.itemsubtotal', 'menu.nm', 'menu.num', 'menu.price',
+                'menu.sub.cnt', 'menu.sub.nm', 'menu.sub.price', 'menu.sub.unitprice', 'menu.unitprice', 'menu.vatyn',
+                'sub_total.discount_price', 'sub_total.etc', 'sub_total.othersvc_price', 'sub_total.service_price',
+                'sub_total.subtotal_price', 'sub_total.tax_price', 'total.cashprice', 'total.changeprice',
+                'total.creditcardprice', 'total.emoneyprice', 'total.menuqty_cnt', 'total.menutype_cnt', 'total.total_etc',
+                'total.total_price', 'void_menu.nm', 'void_menu.price']
+CLASSES_SROIE = ['company', 'address', 'date', 'total']
+
+
 @dataclass
 class OmniVocab:
     """Same derivation as DefaultParser.parse_args (utils/parser.py:88-105)."""
@@ -30,8 +41,11 @@ class OmniVocab:
     pt_seq_length: int = 1024
     vie_categories: int = 0
     use_char_window_prompt: bool = True
+    classes: Optional[List[str]] = None   # KIE entity names; default: SROIE for 4 categories, CORD for 29
 
     def __post_init__(self):
+        if self.vie_categories and self.classes is None:
+            self.classes = {4: CLASSES_SROIE, 29: CLASSES_CORD}.get(self.vie_categories)
         n_char = len(self.chars) + 1
         self.recog_pad_index = self.num_bins + n_char
         self.pt_eos_index = self.recog_pad_index + 1
@@ -149,6 +163,61 @@ class OmniParserB200:
                          [torch.from_numpy(prob[b, :n].copy())]))
         return outs
 
+    def decode_kie(self, image_sizes, pt_prompt: Optional[torch.Tensor] = None):
+        """KIE decoding of every encoded image (model/transformer.py:143-217): per image the reference's
+        ``[(text, class_name, prob, [[x0,y0,x1,y1], ...]), ...]``.  image_sizes: (h, w) per image (seq[3])."""
+        v = self.vocab
+        assert v.vie_categories > 0 and v.classes is not None and len(v.classes) == v.vie_categories
+        B, _, _ = self.memory_shape()
+        prompt = (pt_prompt if pt_prompt is not None else v.pt_prompt()).reshape(-1).to(torch.long).cpu().contiguous()
+        maxi, L, P = max(1, v.pt_seq_length // 2), v.rec_length, v.pt_seq_length
+        n_tok = np.zeros(B, dtype=np.int32)
+        toks = np.zeros((B, P), dtype=np.int64)
+        tprob = np.zeros((B, P), dtype=np.float32)
+        n_inst = np.zeros(B, dtype=np.int32)
+        pos = np.zeros((B, maxi), dtype=np.int32)
+        poly = np.zeros((B, maxi, 32), dtype=np.int64)
+        rec = np.zeros((B, maxi, L), dtype=np.int64)
+        prob = np.zeros((B, maxi, L), dtype=np.float32)
+        cfg = self._cfg(maxi)
+        self.ctx.check(self.lib.alm_omni_decode_kie(self.ctx.h, prompt.data_ptr(), prompt.numel(), C.byref(cfg),
+                                                    n_tok.ctypes.data, toks.ctypes.data, tprob.ctypes.data,
+                                                    n_inst.ctypes.data, pos.ctypes.data, poly.ctypes.data, rec.ctypes.data,
+                                                    prob.ctypes.data))
+        self.last_kie_raw = dict(n_tok=n_tok, tokens=toks, probs=tprob, n_inst=n_inst, inst_pos=pos, poly=poly, rec=rec)
+        results = []
+        for b in range(B):
+            if n_tok[b] == 0:
+                results.append(None)  # transformer.py:240-241
+                continue
+            h, w = [float(x) for x in image_sizes[b]]
+            by_pos = {int(pos[b, n]): n for n in range(int(n_inst[b]))}
+            out, words, rects = [], [], []
+            i = 0
+            while i < n_tok[b]:
+                if i in by_pos:  # an (x, y) pair: polygon extent (:163-169) + transcription (:187-203)
+                    n = by_pos[i]
+                    pts = poly[b, n].reshape(-1, 2)
+                    rects.append([w * float(pts[:, 0].min()) / v.num_bins, h * float(pts[:, 1].min()) / v.num_bins,
+                                  w * float(pts[:, 0].max()) / v.num_bins, h * float(pts[:, 1].max()) / v.num_bins])
+                    chars = []
+                    for tok in rec[b, n].tolist():
+                        if tok == v.recog_pad_index or tok == v.rec_eos_index:
+                            break
+                        if tok == v.recog_pad_index - 1:
+                            continue
+                        chars.append(v.chars[tok - v.num_bins])
+                    words.append(''.join(chars))
+                    i += 2
+                elif toks[b, i] < v.num_bins:
+                    i += 1
+                else:  # class token closes the entity (:211-215)
+                    out.append((' '.join(words), v.classes[int(toks[b, i]) - v.padding_index - 1], float(tprob[b, i]), rects))
+                    words, rects = [], []
+                    i += 1
+            results.append(out)
+        return results
+
     def decode_logits(self, image: int, kind: str, seq: torch.Tensor) -> torch.Tensor:
         """Teacher-forced ``Transformer.decode`` (model/transformer.py:74-100): seq [n,len] -> [n,len,V]."""
         k = {'pt': 0, 'poly': 1, 'rec': 2}[kind]
@@ -178,4 +247,10 @@ class OmniParserB200:
             if int(sequence[1].reshape(-1)[0]) != v.poly_sos_index or int(sequence[2].reshape(-1)[0]) != v.rec_sos_index:
                 raise ValueError('poly/rec prompts must be the sos tokens of the vocabulary (engine/val.py:30-31)')
         self.encode(samples.tensors, samples.mask)
+        if self.vocab.vie_categories:
+            if sequence is None or len(sequence) < 4:
+                raise ValueError('KIE needs the original image size as sequence[3] (engine/val.py:33)')
+            size = sequence[3]
+            sizes = [size] * samples.tensors.shape[0] if torch.as_tensor(size).dim() == 1 else size
+            return self.decode_kie([tuple(float(x) for x in torch.as_tensor(sz).reshape(-1)[:2]) for sz in sizes], pt_prompt)
         return self.decode(pt_prompt)

@@ -144,6 +144,18 @@ ALM_API int alm_omni_memory_shape(alm_ctx* ctx, int* B, int* h, int* w);
 ALM_API int alm_omni_decode(alm_ctx* ctx, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_inst,
                     int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);
 
+/* KIE variant (--infer_vie): replaces the eval branch with `decode_vie_pt_poly_rec_seq` (transformer.py:143-217,243-246).
+ * The pt loop emits (x, y, class) triples (:117-123) with the class slot restricted to the last vie_categories
+ * ids; every (x, y) pair found by the reference's walk (:148-210) gets a polygon and a transcription whose
+ * softmax runs over the first V - vie_categories logits (:156,176).  Outputs (host), per image b:
+ *   n_tok[b]; pt_tokens[b, pt_seq_length] int64 and pt_probs[b, pt_seq_length] f32 (prompt stripped, :132-141);
+ *   n_inst[b]; inst_pos[b, max_inst] = index in pt_tokens where the pair starts;
+ *   poly[b, max_inst, 32], rec[b, max_inst, rec_length], rec_prob[b, max_inst, rec_length].
+ * The entity grouping / class names / rectangles (:163-169,190-215) are plain host post-processing over these. */
+ALM_API int alm_omni_decode_kie(alm_ctx* ctx, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg,
+                                int32_t* n_tok, int64_t* pt_tokens, float* pt_probs, int32_t* n_inst, int32_t* inst_pos,
+                                int64_t* poly, int64_t* rec, float* rec_prob);
+
 /* Teacher-forced logits: replaces `Transformer.decode(input_seq, memory, mask, pos_embed, input_type)`
  * (transformer.py:74-100) for image `image`: seq int64 [n_seq, len] -> logits f32 [n_seq, len, V].
  * kind: 0 = pt, 1 = poly, 2 = rec. */

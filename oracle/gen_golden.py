@@ -146,6 +146,51 @@ def gen_omni():
         print(f'omni_{name}: ok  hw={h}x{w}  out={"None" if out is None else tuple(out[0][2].shape)}')
 
 
+KIE_CASES = {'kie': dict(seed=1010, canvas=(64, 96), wseed=2, pt_eos_bias=-30.0, pt_seq_length=9, rec_length=25, vie=4)}
+
+
+def gen_kie():
+    """KIE branch (--infer_vie --vie_categories 4, SROIE classes): reference Transformer.forward vs restatement."""
+    sys.path[:0] = [SHIM, os.path.join(REF, 'OmniParser')]
+    tmp = tempfile.mktemp(suffix='.pth')
+    torch.save({'model': {}}, tmp)
+    from oracle import omniparser_ref as O
+    from oracle import weights as W
+    from advancedliteratemachinery_b200.omniparser import CLASSES_SROIE
+    for name, case in KIE_CASES.items():
+        sys.argv = ['x', '--tfm_pre_norm', '--use_fpn', '--use_char_window_prompt', '--pretrained_file', tmp,
+                    '--pt_seq_length', str(case['pt_seq_length']), '--rec_length', str(case['rec_length']), '--infer_vie',
+                    '--vie_categories', str(case['vie']), '--val_dataset', 'sroie_test']
+        from utils.parser import DefaultParser
+        from utils.nested_tensor import NestedTensor
+        from model.backbone import build_backbone
+        from model.transformer import build_transformer
+        from model.omniparser import OmniParser
+        args = DefaultParser().parse_args()
+        sd = W.omniparser_state_dict(seed=case['wseed'], vie_categories=case['vie'], pt_eos_bias=case['pt_eos_bias'])
+        model = OmniParser(build_backbone(args), build_transformer(args), args.num_classes, True).eval()
+        r = model.load_state_dict(sd, strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        assert [model.transformer.index2class[W.PADDING + 1 + i] for i in range(4)] == CLASSES_SROIE
+        img, mask = omni_inputs(case)
+        pt_prompt, poly_prompt, rec_prompt = O.default_prompts(True)
+        size = torch.tensor(case['canvas'])
+        with torch.no_grad():
+            out = model(NestedTensor(img, mask), [pt_prompt, poly_prompt, rec_prompt, size])
+            mem, pos, kpm, _ = O.encode(img, mask, sd)
+            res, (pt_seq, pt_probs) = O.greedy_kie(mem[0], kpm[0], pos[0], sd, pt_prompt, case['pt_seq_length'],
+                                                   case['rec_length'], case['vie'], size, CLASSES_SROIE)
+        assert out is not None and len(out) == len(res) and len(out) > 0, (out, res)
+        for a, b in zip(out, res):
+            assert a[0] == b[0] and a[1] == b[1] and abs(a[2] - b[2]) < 1e-5, (a, b)
+            assert np.allclose(np.array(a[3]), np.array(b[3])), (a, b)
+        np.savez_compressed(os.path.join(GOLD, f'omni_{name}.npz'), texts=np.array([a[0] for a in out]),
+                            classes=np.array([a[1] for a in out]), probs=np.array([a[2] for a in out]),
+                            rects=np.array([a[3] for a in out], dtype=np.float64), pt_seq=pt_seq.numpy(),
+                            pt_probs=torch.cat(pt_probs).reshape(-1).numpy())
+        print(f'omni_{name}: ok  entities={[(a[0], a[1]) for a in out]}')
+
+
 MGP_CASES = {'b1': dict(seed=0, batch=1, wseed=0), 'b3': dict(seed=1, batch=3, wseed=0)}
 
 
@@ -186,9 +231,11 @@ if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
     if which == 'all':
-        for w in ('omni', 'mgp'):
+        for w in ('omni', 'kie', 'mgp'):
             subprocess.check_call([sys.executable, '-m', 'oracle.gen_golden', w], cwd=REPO)
     elif which == 'omni':
         gen_omni()
+    elif which == 'kie':
+        gen_kie()
     else:
         gen_mgp()

@@ -338,6 +338,75 @@ def greedy_text_spotting(memory, mem_kpm, pos, sd, pt_prompt, pt_seq_length, rec
     return (res, logs) if return_logits else res
 
 
+def greedy_kie(memory, mem_kpm, pos, sd, pt_prompt, pt_seq_length, rec_length, vie, image_size, classes):
+    """KIE eval branch for ONE image: decode_pt_seq with infer_vie (transformer.py:102-141, :117-123) followed by
+    decode_vie_pt_poly_rec_seq (:143-217).  Returns None when no token is produced, else the reference's
+    ``[(text, class_name, prob, [[x0,y0,x1,y1], ...]), ...]``; second value = raw (pt_seq, pt_probs)."""
+    nb, eos = W.NUM_BINS, W.PT_EOS
+    n_prompt = pt_prompt.shape[1]
+    pt_seq, pt_probs = pt_prompt, []
+    for i in range(pt_seq_length):
+        out = decode_logits(pt_seq, memory, mem_kpm, pos, sd, 'pt')[:, -1, :].softmax(-1)
+        if i % 3 == 0:
+            out[:, nb:eos] = 0
+            out[:, eos + 1:] = 0
+        elif i % 3 == 1:
+            out = out[:, :nb]
+        else:
+            out[:, :-vie] = 0
+        prob, extra = out.topk(dim=-1, k=1)
+        if extra[0] == eos:
+            break
+        pt_seq = torch.cat([pt_seq, extra], dim=-1)
+        pt_probs.append(prob)
+    pt_seq = pt_seq[:, n_prompt:]
+    if pt_seq.shape[1] % 2 != 0:
+        pt_seq = pt_seq[:, :-1]
+    pt_seq = pt_seq[0]
+    if pt_seq.numel() == 0:
+        return None, (pt_seq, pt_probs)
+    image_h, image_w = image_size
+    result, tmp_recog, tmp_rect = [], [], []
+    i = 0
+    while i < len(pt_seq):
+        if pt_seq[i].item() < nb:
+            if i + 1 <= len(pt_seq) - 1 and pt_seq[i + 1].item() < nb:
+                poly_seq = torch.cat((pt_seq[i:i + 2].unsqueeze(0), torch.tensor([[W.POLY_SOS]])), dim=-1)
+                for _ in range(32):
+                    lg = decode_logits(poly_seq, memory, mem_kpm, pos, sd, 'poly')[:, -1, :-vie]
+                    _, extra = lg.softmax(-1)[:, :nb].topk(dim=-1, k=1)
+                    poly_seq = torch.cat([poly_seq, extra], dim=-1)
+                pts = poly_seq[0, 3:35].reshape(-1, 2)
+                rect = [image_w * pts[:, 0].min().item() / nb, image_h * pts[:, 1].min().item() / nb,
+                        image_w * pts[:, 0].max().item() / nb, image_h * pts[:, 1].max().item() / nb]
+                rec_seq = torch.cat((pt_seq[i:i + 2].unsqueeze(0), torch.tensor([[W.REC_SOS]])), dim=-1)
+                for _ in range(rec_length):
+                    out = decode_logits(rec_seq, memory, mem_kpm, pos, sd, 'rec')[:, -1, :-vie].softmax(-1)
+                    out[:, :nb] = 0
+                    out[:, W.PT_EOS] = 0
+                    out[:, W.POLY_EOS] = 0
+                    out[:, W.REC_EOS + 1:] = 0
+                    _, extra = out.topk(dim=-1, k=1)
+                    rec_seq = torch.cat([rec_seq, extra], dim=-1)
+                recog = []
+                for tok in rec_seq[0, 3:].tolist():
+                    if tok == W.RECOG_PAD or tok == W.REC_EOS:
+                        break
+                    if tok == W.RECOG_PAD - 1:
+                        continue
+                    recog.append(W.CHARS[tok - nb])
+                tmp_recog.append(''.join(recog))
+                tmp_rect.append(rect)
+                i += 2
+            else:
+                i += 1
+        else:
+            result.append((' '.join(tmp_recog), classes[pt_seq[i].item() - W.PADDING - 1], pt_probs[i].item(), tmp_rect))
+            i += 1
+            tmp_recog, tmp_rect = [], []
+    return result, (pt_seq, pt_probs)
+
+
 def forward(img, mask, sd, pt_seq_length, rec_length=25, use_char_window_prompt=True):
     """OmniParser.forward (omniparser.py:19-32) for a batch of independent batch-1 problems
     (the reference only supports batch 1, engine/val.py:22).  Returns a list per image."""

@@ -262,3 +262,29 @@ def test_error_paths():
     with pytest.raises(AlmError):
         c.set_option('nsplit', 2)
     c.close()
+
+
+def test_kie_decode_matches_reference_fixture(golden_dir):
+    """--infer_vie branch (transformer.py:143-217): (x, y, class) point loop, per-pair polygon + transcription
+    with the class logits excluded from the softmax, entity grouping."""
+    from advancedliteratemachinery_b200 import NestedTensor, OmniParserB200, OmniVocab
+    from advancedliteratemachinery_b200 import synthetic as W
+    from oracle.gen_golden import KIE_CASES, omni_inputs
+    case = KIE_CASES['kie']
+    gold = np.load(os.path.join(golden_dir, 'omni_kie.npz'))
+    for k in list(_MODELS):
+        _MODELS.pop(k).ctx.close()
+    sd = W.omniparser_state_dict(seed=case['wseed'], vie_categories=case['vie'], pt_eos_bias=case['pt_eos_bias'])
+    v = OmniVocab(vie_categories=case['vie'], pt_seq_length=case['pt_seq_length'], rec_length=case['rec_length'])
+    m = OmniParserB200(sd, v, workspace_mb=8192)
+    img, mask = omni_inputs(case)
+    seqs = [v.pt_prompt(), torch.tensor([[v.poly_sos_index]]), torch.tensor([[v.rec_sos_index]]), torch.tensor(case['canvas'])]
+    out = m(NestedTensor(img, mask), seqs)
+    assert [r[0] for r in out] == gold['texts'].tolist()
+    assert [r[1] for r in out] == gold['classes'].tolist()
+    np.testing.assert_allclose(np.array([r[2] for r in out]), gold['probs'], rtol=2e-3)
+    np.testing.assert_allclose(np.array([r[3] for r in out]), gold['rects'])
+    raw = m.last_kie_raw
+    assert np.array_equal(raw['tokens'][0, :raw['n_tok'][0]], gold['pt_seq'])
+    np.testing.assert_allclose(raw['probs'][0, :raw['n_tok'][0]], gold['pt_probs'][:raw['n_tok'][0]], rtol=2e-3)
+    m.ctx.close()

@@ -64,3 +64,21 @@ def test_vocab_layout():
     assert (W.RECOG_PAD, W.PT_EOS, W.POLY_EOS, W.REC_EOS, W.PT_SOS, W.POLY_SOS, W.REC_SOS, W.PADDING) == \
            (1096, 1097, 1098, 1099, 1100, 1101, 1102, 1103)
     assert len(W.CHARS) == 95
+
+
+def test_kie_oracle_matches_reference_fixture(golden_dir):
+    """decode_vie_pt_poly_rec_seq restatement vs the fixture written from the reference (SROIE classes)."""
+    from advancedliteratemachinery_b200.omniparser import CLASSES_SROIE
+    from advancedliteratemachinery_b200 import synthetic as W
+    from oracle.gen_golden import KIE_CASES
+    case = KIE_CASES['kie']
+    gold = np.load(os.path.join(golden_dir, 'omni_kie.npz'))
+    sd = W.omniparser_state_dict(seed=case['wseed'], vie_categories=case['vie'], pt_eos_bias=case['pt_eos_bias'])
+    img, mask = omni_inputs(case)
+    mem, pos, kpm, _ = O.encode(img, mask, sd)
+    res, (pt_seq, pt_probs) = O.greedy_kie(mem[0], kpm[0], pos[0], sd, O.default_prompts(True)[0], case['pt_seq_length'],
+                                           case['rec_length'], case['vie'], torch.tensor(case['canvas']), CLASSES_SROIE)
+    assert [r[0] for r in res] == gold['texts'].tolist()
+    assert [r[1] for r in res] == gold['classes'].tolist()
+    assert np.array_equal(pt_seq.numpy(), gold['pt_seq'])
+    np.testing.assert_allclose(np.array([r[3] for r in res]), gold['rects'])
