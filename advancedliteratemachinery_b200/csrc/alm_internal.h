@@ -154,6 +154,8 @@ struct Ctx {
     }
   };
   std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
+  int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
+  int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial
   int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps
   unsigned long long* trace_buf = nullptr;  // optional in-kernel GEMM timeline (alm_set_option "trace_gemm")
   int* trace_idx = nullptr;
@@ -188,7 +190,11 @@ int* upload_i32(Ctx* c, const std::vector<int>& v);
 // zero_missing: a row whose (single) source is -1 is written as zeros *without* LN/affine ("pad after norm").
 void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int Cs, long rows, const float* gamma,
                const float* beta, float eps, bool zero_missing, const float* add, long ld_add, float* out_f32,
-               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo);
+               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo,
+               float* out2_f32 = nullptr);
+
+void gemv_rows(Ctx* c, const float* x, long ldx, const float* W, const float* bias, const float* resid, long ldr,
+               float* out, long ldo, int M, int N, int K, int act);
 
 void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp, bf16* hi, bf16* lo);
 

@@ -176,6 +176,11 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
       }
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
+    } else if (k == "wide_tiles") {
+      h->c.wide_tiles = value ? 1 : 0;
+    } else if (k == "decode_streams") {
+      ALM_REQUIRE(value == 1 || value == 2, ALM_ERR_INVALID, "decode_streams must be 1 or 2");
+      h->c.decode_streams = static_cast<int>(value);
     } else if (k == "use_graphs") {
       h->c.use_graphs = value ? 1 : 0;
     } else if (k == "profile_gemm") {

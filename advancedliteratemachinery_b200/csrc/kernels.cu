@@ -41,7 +41,7 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int zero_missing,
                  const float* __restrict__ add, long ld_add, float* __restrict__ out_f32, long ldo_f32,
                  bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, long ldo_bf, bf16* __restrict__ out2_hi,
-                 bf16* __restrict__ out2_lo) {
+                 bf16* __restrict__ out2_lo, float* __restrict__ out2_f32) {
   const long r = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -89,13 +89,14 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
     const int e = 4 * (lane + 32 * j);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ldo_f32 + e) = v[j];
     if (out_hi) store_split4(out_hi, out_lo, r * ldo_bf + e, v[j]);
-    if (out2_hi) {
+    if (out2_hi || out2_f32) {
       float4 y = v[j];
       if (add) {
         const float4 a = *reinterpret_cast<const float4*>(add + r * ld_add + e);
         y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
       }
-      store_split4(out2_hi, out2_lo, r * ldo_bf + e, y);
+      if (out2_hi) store_split4(out2_hi, out2_lo, r * ldo_bf + e, y);
+      if (out2_f32) *reinterpret_cast<float4*>(out2_f32 + r * ldo_f32 + e) = y;
     }
   }
 }
@@ -468,11 +469,62 @@ softmax_rows_kernel(const float* __restrict__ s, long lds, int n, const uint8_t*
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Skinny fp32 linear for the single-sequence-per-image decode (M <= 32 rows): out[m, n] = act(x[m,:].W[n,:] + b[n])
+// (+ resid[m, n]).  One warp per output column streams its fp32 weight row once (coalesced float4) while the few
+// activation rows come from L1; a tensor-core tile would be > 90 % padding here and the op is latency-bound anyway.
+// Weights stay exact fp32, so this path is closer to the reference than the split-bf16 GEMM.
+// ---------------------------------------------------------------------------------------------
+template <int MR, int NW>  // MR = row capacity (8/16/32), NW = K / 128 float4 slices of the weight row per lane
+__global__ void __launch_bounds__(128)
+gemv_rows_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                 const float* __restrict__ resid, long ldr, float* __restrict__ out, long ldo, int M, int N, int K,
+                 int act) {
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  // the whole weight row of this column is requested up front (NW independent 16-byte loads per lane = one HBM
+  // round trip); the activation rows are then read from L1/L2
+  float4 w[NW];
+  const float* wrow = W + static_cast<long>(n) * K;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    const int k0 = (i * 32 + lane) * 4;
+    w[i] = k0 < K ? *reinterpret_cast<const float4*>(wrow + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int m = 0; m < MR; ++m) {
+    float acc = 0.f;
+    if (m < M) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const int k0 = (i * 32 + lane) * 4;
+        if (k0 < K) {
+          const float4 a = *reinterpret_cast<const float4*>(x + m * ldx + k0);
+          acc = fmaf(a.x, w[i].x, acc); acc = fmaf(a.y, w[i].y, acc);
+          acc = fmaf(a.z, w[i].z, acc); acc = fmaf(a.w, w[i].w, acc);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == m) mine = acc;
+  }
+  if (lane < M && lane < MR) {
+    float v = mine + (bias ? bias[n] : 0.f);
+    if (act == ACT_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+    if (resid) v += resid[lane * ldr + n];
+    out[lane * ldo + n] = v;
+  }
+}
+
 }  // namespace
 
 void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int Cs, long rows, const float* gamma,
                const float* beta, float eps, bool zero_missing, const float* add, long ld_add, float* out_f32,
-               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo) {
+               long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo, float* out2_f32) {
   if (rows == 0) return;
   const int C = nsrc * Cs;
   ALM_REQUIRE(C % 128 == 0 && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID, "gather_ln: width must be a multiple of 128");
@@ -483,7 +535,7 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
   case NVV:                                                                                                       \
     gather_ln_kernel<NVV><<<grid, block, 0, c->stream>>>(src, lds, map, nsrc, Cs, rows, gamma, beta, eps,         \
                                                          zero_missing ? 1 : 0, add, ld_add, out_f32, ldo_f32,     \
-                                                         out_hi, out_lo, ldo_bf, out2_hi, out2_lo);               \
+                                                         out_hi, out_lo, ldo_bf, out2_hi, out2_lo, out2_f32);     \
     break;
   switch (nv) {
     ALM_GLN(1) ALM_GLN(2) ALM_GLN(3) ALM_GLN(4) ALM_GLN(6) ALM_GLN(8) ALM_GLN(16)
@@ -534,4 +586,22 @@ void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint
   check_launch("softmax_rows");
 }
 
+}  // namespace alm
+
+namespace alm {
+void gemv_rows(Ctx* c, const float* x, long ldx, const float* W, const float* bias, const float* resid, long ldr,
+               float* out, long ldo, int M, int N, int K, int act) {
+  ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048, ALM_ERR_INVALID,
+              "gemv_rows: M <= 32, K % 4 == 0, K <= 2048");
+  const unsigned grid = static_cast<unsigned>((N + 3) / 4);
+#define ALM_GEMV(MRV, NWV) \
+  gemv_rows_kernel<MRV, NWV><<<grid, 128, 0, c->stream>>>(x, ldx, W, bias, resid, ldr, out, ldo, M, N, K, act)
+  const int nw = K <= 512 ? 4 : 16;
+  if (M <= 8) { if (nw == 4) ALM_GEMV(8, 4); else ALM_GEMV(8, 16); }
+  else if (M <= 16) { if (nw == 4) ALM_GEMV(16, 4); else ALM_GEMV(16, 16); }
+  else { if (nw == 4) ALM_GEMV(32, 4); else ALM_GEMV(32, 16); }
+#undef ALM_GEMV
+  count_launch(c);
+  check_launch("gemv_rows");
+}
 }  // namespace alm

@@ -32,12 +32,13 @@ LNW load_ln(Ctx* c, const std::map<std::string, HostTensor>& t, const std::strin
 }
 
 Lin load_lin(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int N, int K, bool bias = true,
-             int Kpad = 0) {
+             int Kpad = 0, bool keep_f32 = false) {
   const HostTensor& w = need(t, p + ".weight");
   ALM_REQUIRE(static_cast<long>(w.numel()) == static_cast<long>(N) * K, ALM_ERR_INVALID,
               "Linear weight shape mismatch at " + p);
   Lin l;
   l.w = upload_split(c, w.f32.data(), N, K, Kpad);
+  if (keep_f32) l.wf = upload_f32(c, w.f32.data(), w.numel());
   if (bias) {
     const HostTensor& b = need(t, p + ".bias");
     ALM_REQUIRE(static_cast<int>(b.numel()) == N, ALM_ERR_INVALID, "Linear bias shape mismatch at " + p);
@@ -53,6 +54,7 @@ Lin load_inproj_rows(Ctx* c, const std::map<std::string, HostTensor>& t, const s
   ALM_REQUIRE(w.numel() == size_t(1536) * 512 && b.numel() == 1536, ALM_ERR_INVALID, "in_proj shape mismatch at " + p);
   Lin l;
   l.w = upload_split(c, w.f32.data() + static_cast<size_t>(r0) * 512, n, 512, 0);
+  l.wf = upload_f32(c, w.f32.data() + static_cast<size_t>(r0) * 512, static_cast<size_t>(n) * 512);
   l.b = upload_f32(c, b.f32.data() + r0, n);
   return l;
 }
@@ -170,11 +172,11 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
       w.n3 = load_ln(c, t, p + "norm3", 512);
       w.sa_qk = load_inproj_rows(c, t, p + "self_attn", 0, 1024);
       w.sa_v = load_inproj_rows(c, t, p + "self_attn", 1024, 512);
-      w.sa_out = load_lin(c, t, p + "self_attn.out_proj", 512, 512);
+      w.sa_out = load_lin(c, t, p + "self_attn.out_proj", 512, 512, true, 0, true);
       w.ca_q = load_inproj_rows(c, t, p + "multihead_attn", 0, 512);
-      w.ca_out = load_lin(c, t, p + "multihead_attn.out_proj", 512, 512);
-      w.l1 = load_lin(c, t, p + "linear1", 2048, 512);
-      w.l2 = load_lin(c, t, p + "linear2", 512, 2048);
+      w.ca_out = load_lin(c, t, p + "multihead_attn.out_proj", 512, 512, true, 0, true);
+      w.l1 = load_lin(c, t, p + "linear1", 2048, 512, true, 0, true);
+      w.l2 = load_lin(c, t, p + "linear2", 512, 2048, true, 0, true);
       const HostTensor& ipw = need(t, p + "multihead_attn.in_proj_weight");
       const HostTensor& ipb = need(t, p + "multihead_attn.in_proj_bias");
       const size_t dl = static_cast<size_t>(d) * 4 + l;
@@ -185,9 +187,9 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
     }
     m->dec_norm[d] = load_ln(c, t, tr + kinds[d] + "_decoder.norm", 512);
     const std::string hp = tr + kinds[d] + "_pred_layer.layers.";
-    m->head[d][0] = load_lin(c, t, hp + "0", 512, 512);
-    m->head[d][1] = load_lin(c, t, hp + "1", 512, 512);
-    m->head[d][2] = load_lin(c, t, hp + "2", m->V, 512);
+    m->head[d][0] = load_lin(c, t, hp + "0", 512, 512, true, 0, true);
+    m->head[d][1] = load_lin(c, t, hp + "1", 512, 512, true, 0, true);
+    m->head[d][2] = load_lin(c, t, hp + "2", m->V, 512, true, 0, true);
   }
   m->ca_k_all.w = upload_split(c, kw.data(), 12 * 512, 512, 0);
   m->ca_k_all.b = upload_f32(c, kb.data(), kb.size());
@@ -362,6 +364,8 @@ struct DecodeBufs {
   int* tpos = nullptr;    // device-side position counter (so one captured graph serves every token)
   SplitBuf ln, lnp, att, q, o, hid, h0, h1;
   float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr, *qf = nullptr;
+  float *lnf = nullptr, *lnpf = nullptr, *attf = nullptr, *of = nullptr, *hidf = nullptr, *h0f = nullptr, *h1f = nullptr;
+  bool skinny = false;          // S <= 32 live sequences: all-fp32 SIMT GEMV path instead of tensor-core tiles
   float* xq_partial = nullptr;  // fused single-query cross-attention: split partials + counters
   int* xq_counters = nullptr;
   int xq_splits = 1;
@@ -388,6 +392,12 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
   d.qk = c->ws.get<float>(S * 1024);
   d.v = c->ws.get<float>(S * 512);
   d.qf = c->ws.get<float>(S * 512);
+  d.skinny = (Ncap == 1 && d.S <= 32);
+  if (d.skinny) {
+    d.lnf = c->ws.get<float>(S * 512); d.lnpf = c->ws.get<float>(S * 512); d.attf = c->ws.get<float>(S * 512);
+    d.of = c->ws.get<float>(S * 512); d.hidf = c->ws.get<float>(S * 2048); d.h0f = c->ws.get<float>(S * 512);
+    d.h1f = c->ws.get<float>(S * 512);
+  }
   if (Ncap == 1) {
     d.xq_splits = cross_attn_q1_splits(c, B, m->M);
     d.xq_partial = c->ws.get<float>(static_cast<size_t>(B) * 8 * d.xq_splits * 66);
@@ -413,6 +423,43 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
   const int S = u.S, Ncap = u.Ncap, M = m->M, Mpad = m->Mpad;
   embed_ln(c, tokens, tstride, u.tpos, S, m->word_emb, m->pos_emb[d], m->emb_norm.g, m->emb_norm.b, u.x, u.qpos);
   const float* qpos = u.qpos;
+  if (u.skinny) {
+    // One live sequence per image and at most 32 of them: every linear is a skinny fp32 GEMV (exact fp32 weights,
+    // one warp per output column), no operand splitting, no tensor-core tile padding.
+    auto lin = [&](const float* x, int K, const Lin& w, int act, float* out, const float* resid) {
+      gemv_rows(c, x, K, w.wf, w.b, resid, w.w.N, out, w.w.N, S, w.w.N, K, act);
+    };
+    for (int l = 0; l < 4; ++l) {
+      const DecLayerW& w = m->dec[d][l];
+      const long dl = static_cast<long>(d) * 4 + l;
+      gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n1.g, w.n1.b, 1e-5f, false, qpos, 0, u.lnf, 512, nullptr, nullptr, 512,
+                nullptr, nullptr, u.lnpf);
+      lin(u.lnpf, 512, w.sa_qk, ACT_NONE, u.qk, nullptr);
+      lin(u.lnf, 512, w.sa_v, ACT_NONE, u.v, nullptr);
+      self_attn_step(c, u.qk, u.v, u.kc[l], u.vc[l], S, u.tpos, u.Tmax, nullptr, nullptr, u.attf);
+      lin(u.attf, 512, w.sa_out, ACT_NONE, u.x, u.x);
+      gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n2.g, w.n2.b, 1e-5f, false, qpos, 0, nullptr, 512, nullptr, nullptr, 512,
+                nullptr, nullptr, u.lnpf);
+      lin(u.lnpf, 512, w.ca_q, ACT_NONE, u.qf, nullptr);
+      const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
+      const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
+      cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                    m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, nullptr,
+                    nullptr, u.of);
+      lin(u.of, 512, w.ca_out, ACT_NONE, u.x, u.x);
+      gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n3.g, w.n3.b, 1e-5f, false, nullptr, 0, u.lnf, 512, nullptr, nullptr, 512,
+                nullptr, nullptr);
+      lin(u.lnf, 512, w.l1, ACT_RELU, u.hidf, nullptr);
+      lin(u.hidf, 2048, w.l2, ACT_NONE, u.x, u.x);
+    }
+    if (!want_logits) return;
+    gather_ln(c, u.x, 512, nullptr, 1, 512, S, m->dec_norm[d].g, m->dec_norm[d].b, 1e-5f, false, nullptr, 0, u.lnf, 512,
+              nullptr, nullptr, 512, nullptr, nullptr);
+    lin(u.lnf, 512, m->head[d][0], ACT_RELU, u.h0f, nullptr);
+    lin(u.h0f, 512, m->head[d][1], ACT_RELU, u.h1f, nullptr);
+    lin(u.h1f, 512, m->head[d][2], ACT_NONE, u.logits, nullptr);
+    return;
+  }
   for (int l = 0; l < 4; ++l) {
     const DecLayerW& w = m->dec[d][l];
     const long dl = static_cast<long>(d) * 4 + l;
@@ -645,7 +692,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
     ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
-  cudaStream_t s0 = c->stream, s1 = c->stream2;
+  cudaStream_t s0 = c->stream, s1 = c->decode_streams == 2 ? c->stream2 : c->stream;
   ws.release(after_pt_tokens);
   const int S = B * Ncap;
   int* toks[3] = {nullptr, nullptr, nullptr};

@@ -15,6 +15,7 @@ struct LNW {
 struct Lin {
   SplitW w;
   float* b = nullptr;
+  float* wf = nullptr;  // exact fp32 [N,K] copy (decoder weights only): the skinny M <= 32 decode path
 };
 
 struct SwinBlockW {
@@ -97,13 +98,13 @@ void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, co
 void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, const float* word_emb,
               const float* pos_emb, const float* gamma, const float* beta, float* x, float* qpos);
 void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* tptr, int Tmax,
-                    bf16* out_hi, bf16* out_lo);
+                    bf16* out_hi, bf16* out_lo, float* out_f32 = nullptr);
 void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
                  int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image);
 void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo,
                    const uint8_t* kpm, int nimg, int M, int Mpad, float* partial, int* counters, int nsplit,
-                   bf16* out_hi, bf16* out_lo);
+                   bf16* out_hi, bf16* out_lo, float* out_f32 = nullptr);
 int cross_attn_q1_splits(Ctx* c, int nimg, int M);
 void add_i32(Ctx* c, int* p, int v);
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,

@@ -228,7 +228,7 @@ embed_ln_kernel(const int* __restrict__ tokens, int tstride, const int* __restri
 __global__ void __launch_bounds__(128)
 self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vnew, float* __restrict__ kc,
                       float* __restrict__ vc, int S, const int* __restrict__ tptr, int Tmax, bf16* __restrict__ out_hi,
-                      bf16* __restrict__ out_lo) {
+                      bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
   extern __shared__ float sp[];  // [4 warps][Tmax]
   const int t = *tptr;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,8 +281,11 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
   }
   bf16 hh, ll;
   const long o = static_cast<long>(s) * 512 + h * 64;
-  split_bf16(o0, hh, ll); out_hi[o + lane] = hh; if (out_lo) out_lo[o + lane] = ll;
-  split_bf16(o1, hh, ll); out_hi[o + lane + 32] = hh; if (out_lo) out_lo[o + lane + 32] = ll;
+  if (out_f32) { out_f32[o + lane] = o0; out_f32[o + lane + 32] = o1; }
+  if (out_hi) {
+    split_bf16(o0, hh, ll); out_hi[o + lane] = hh; if (out_lo) out_lo[o + lane] = ll;
+    split_bf16(o1, hh, ll); out_hi[o + lane + 32] = hh; if (out_lo) out_lo[o + lane + 32] = ll;
+  }
 }
 
 // Fused single-query cross-attention for the pt loop (one live sequence per image, transformer.py:444-447):
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(XQ_THREADS)
 cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo,
                      const bf16* __restrict__ vt_hi, const bf16* __restrict__ vt_lo, const uint8_t* __restrict__ kpm,
                      int M, int Mpad, int keys_per_split, float* __restrict__ partial, int* __restrict__ counters,
-                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
   extern __shared__ float xs[];            // [keys_per_split] scores / probabilities
   __shared__ float sq[64];
   __shared__ float red[XQ_THREADS / 32];
@@ -402,10 +405,14 @@ cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi
   const long obase = static_cast<long>(img) * 512 + h * 64;
   if (nsplit == 1) {
     if (part == 0) {
-      bf16 hh, ll;
-      split_bf16(acc / l, hh, ll);
-      out_hi[obase + d] = hh;
-      if (out_lo) out_lo[obase + d] = ll;
+      const float y = acc / l;
+      if (out_f32) out_f32[obase + d] = y;
+      if (out_hi) {
+        bf16 hh, ll;
+        split_bf16(y, hh, ll);
+        out_hi[obase + d] = hh;
+        if (out_lo) out_lo[obase + d] = ll;
+      }
     }
     return;
   }
@@ -430,10 +437,14 @@ cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi
       ltot += w * base[sidx * 66 + 1];
       otot += w * base[sidx * 66 + 2 + t];
     }
-    bf16 hh, ll;
-    split_bf16(otot / ltot, hh, ll);
-    out_hi[obase + t] = hh;
-    if (out_lo) out_lo[obase + t] = ll;
+    const float y = otot / ltot;
+    if (out_f32) out_f32[obase + t] = y;
+    if (out_hi) {
+      bf16 hh, ll;
+      split_bf16(y, hh, ll);
+      out_hi[obase + t] = hh;
+      if (out_lo) out_lo[obase + t] = ll;
+    }
   }
   if (t == 0) counters[pair] = 0;  // ready for the next launch
 }
@@ -580,11 +591,11 @@ void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, co
   count_launch(c); check_launch("embed_ln");
 }
 void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* t, int Tmax,
-                    bf16* out_hi, bf16* out_lo) {
+                    bf16* out_hi, bf16* out_lo, float* out_f32) {
   const long groups = static_cast<long>(S) * 8;
   const size_t sm = static_cast<size_t>(4) * Tmax * sizeof(float);
   self_attn_step_kernel<<<static_cast<unsigned>((groups + 3) / 4), 128, sm, c->stream>>>(qk, vnew, kc, vc, S, t, Tmax,
-                                                                                        out_hi, out_lo);
+                                                                                        out_hi, out_lo, out_f32);
   count_launch(c); check_launch("self_attn_step");
 }
 void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
@@ -602,7 +613,7 @@ void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_promp
 }
 void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo,
                    const uint8_t* kpm, int nimg, int M, int Mpad, float* partial, int* counters, int nsplit,
-                   bf16* out_hi, bf16* out_lo) {
+                   bf16* out_hi, bf16* out_lo, float* out_f32) {
   int kps = (M + nsplit - 1) / nsplit;
   kps = (kps + 7) & ~7;
   const size_t sm = static_cast<size_t>(kps) * sizeof(float);
@@ -614,11 +625,11 @@ void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo,
   }
   dim3 grid(nimg * 8, nsplit);
   cross_attn_q1_kernel<<<grid, XQ_THREADS, sm, c->stream>>>(q, kc_hi, kc_lo, vt_hi, vt_lo, kpm, M, Mpad, kps, partial,
-                                                            counters, out_hi, out_lo);
+                                                            counters, out_hi, out_lo, out_f32);
   count_launch(c); check_launch("cross_attn_q1");
 }
 int cross_attn_q1_splits(Ctx* c, int nimg, int M) {
-  int ns = (2 * c->num_sms + nimg * 8 - 1) / (nimg * 8);
+  int ns = (6 * c->num_sms + nimg * 8 - 1) / (nimg * 8);  // ~6 resident CTAs per SM keep HBM busy across phases
   ns = std::max(1, std::min(ns, 16));
   while (ns > 1 && (M + ns - 1) / ns < 256) --ns;
   return ns;

@@ -80,6 +80,8 @@ ALM_API const char* alm_version(void);
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
  *          "trace_gemm" (capacity; see alm_trace_read), "trace_detail" (see alm_bench_gemm_ex),
  *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
+ *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
+ *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
 /* kernels launched on this context since the last call with reset != 0 */
