@@ -46,6 +46,7 @@ SIGNATURES = {
     'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
     'alm_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'alm_trace_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    'alm_bench_graph_floor': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     'alm_bench_gemm_ex': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_float), C.c_void_p]),
     'alm_bench_gemm': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -60,6 +61,7 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'alm_omni_decode_logits': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'alm_omni_vocab': (C.c_int, [C.c_void_p]),
+    'alm_omni_last_timing': (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'alm_mgpstr_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     'alm_op_linear': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -118,6 +120,11 @@ class Context:
         n = C.c_int()
         self.check(self.lib.alm_trace_read(self.h, buf.ctypes.data, max_records, C.byref(n)))
         return buf[:n.value]
+
+    def omni_last_timing(self):
+        e, p, r = C.c_float(), C.c_float(), C.c_float()
+        self.check(self.lib.alm_omni_last_timing(self.h, C.byref(e), C.byref(p), C.byref(r)))
+        return {'encode_ms': e.value, 'pt_loop_ms': p.value, 'poly_rec_loops_ms': r.value}
 
     def bench_gemm_ex(self, M, N, K, batch=1, split_out=0, act=0, iters=10, detail=False):
         import numpy as np

@@ -128,6 +128,8 @@ struct Ctx {
   bool own_stream = false;
   cudaStream_t stream2 = nullptr;  // second stream: the poly and rec decode loops overlap
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_t[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // encode start/end, decode start, pt end, decode end
+  bool timing_valid[2] = {false, false};
   int num_sms = 148;
   std::string err;
   Arena ws;
@@ -154,6 +156,7 @@ struct Ctx {
     }
   };
   std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
+  int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
   int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial
   int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps
@@ -193,8 +196,8 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
                long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo,
                float* out2_f32 = nullptr);
 
-void gemv_rows(Ctx* c, const float* x, long ldx, const float* W, const float* bias, const float* resid, long ldr,
-               float* out, long ldo, int M, int N, int K, int act);
+void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, const float* W, const float* bias,
+               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act);
 
 void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp, bf16* hi, bf16* lo);
 
@@ -205,6 +208,21 @@ void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, 
 
 void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint8_t* kpm, int rows_per_mask,
                   long mask_ld, float* out_f32, bf16* out_hi, bf16* out_lo, long ldo);
+
+// Every kernel of the per-token decode loop asks for the same (maximum) shared-memory carve-out: consecutive kernels
+// with different L1/shared splits force an SM reconfiguration (the SM must drain) between every pair of launches.
+template <class F>
+inline void pin_carveout(F* kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define ALM_PIN_CARVEOUT(kernel)            \
+  do {                                      \
+    static bool pinned_ = false;            \
+    if (!pinned_) {                         \
+      alm::pin_carveout(kernel);            \
+      pinned_ = true;                       \
+    }                                       \
+  } while (0)
 
 void count_launch(Ctx* c, int n = 1);
 void check_launch(const char* what);

@@ -9,6 +9,7 @@
 
 using namespace alm;
 
+
 struct alm_ctx {
   Ctx c;
   void* dev_in = nullptr;  // staging for host-resident inputs
@@ -145,6 +146,7 @@ void alm_free(alm_ctx* h) {
   if (h->dev_mask) cudaFree(h->dev_mask);
   if (h->c.stream2) cudaStreamDestroy(h->c.stream2);
   if (h->c.ev_fork) { cudaEventDestroy(h->c.ev_fork); cudaEventDestroy(h->c.ev_join); }
+  for (auto e : h->c.ev_t) if (e) cudaEventDestroy(e);
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
   delete h;
 }
@@ -176,6 +178,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
       }
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
+    } else if (k == "small_grid_cap") {
+      h->c.small_grid_cap = static_cast<int>(value);
     } else if (k == "wide_tiles") {
       h->c.wide_tiles = value ? 1 : 0;
     } else if (k == "decode_streams") {
@@ -230,6 +234,38 @@ int alm_trace_read(alm_ctx* h, unsigned long long* out, int max_records, int* n_
     ALM_CHECK_CUDA(cudaMemcpy(out, h->c.trace_buf, static_cast<size_t>(n) * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     ALM_CHECK_CUDA(cudaMemset(h->c.trace_idx, 0, sizeof(int)));
     *n_records = n;
+  });
+}
+
+int alm_bench_graph_floor(alm_ctx* h, int nodes, int iters, float* us_per_node) {
+  // replay cost of a captured chain of `nodes` trivial dependent kernels: the per-kernel floor of the decode loop
+  return guarded(h, [&] {
+    ALM_REQUIRE(nodes > 0 && iters > 0 && us_per_node, ALM_ERR_INVALID, "alm_bench_graph_floor arguments");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    int* p = c->ws.get<int>(4);
+    ALM_CHECK_CUDA(cudaMemsetAsync(p, 0, 16, c->stream));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    ALM_CHECK_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < nodes; ++i) fill_i32(c, p, 1, i);
+    ALM_CHECK_CUDA(cudaStreamEndCapture(c->stream, &g));
+    ALM_CHECK_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    for (int i = 0; i < 3; ++i) ALM_CHECK_CUDA(cudaGraphLaunch(ge, c->stream));
+    cudaEvent_t e0, e1;
+    ALM_CHECK_CUDA(cudaEventCreate(&e0));
+    ALM_CHECK_CUDA(cudaEventCreate(&e1));
+    ALM_CHECK_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; ++i) ALM_CHECK_CUDA(cudaGraphLaunch(ge, c->stream));
+    ALM_CHECK_CUDA(cudaEventRecord(e1, c->stream));
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    ALM_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *us_per_node = ms * 1e3f / (static_cast<float>(iters) * nodes);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(ge);
+    c->ws.release(mk);
   });
 }
 
@@ -366,6 +402,21 @@ int alm_omni_memory_shape(alm_ctx* h, int* B, int* mh, int* mw) {
     if (B) *B = h->c.omni->B;
     if (mh) *mh = h->c.omni->mh;
     if (mw) *mw = h->c.omni->mw;
+  });
+}
+
+int alm_omni_last_timing(alm_ctx* h, float* encode_ms, float* pt_ms, float* polyrec_ms) {
+  return guarded(h, [&] {
+    ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream));
+    float e = -1.f, p = -1.f, r = -1.f;
+    if (h->c.timing_valid[0]) ALM_CHECK_CUDA(cudaEventElapsedTime(&e, h->c.ev_t[0], h->c.ev_t[1]));
+    if (h->c.timing_valid[1]) {
+      ALM_CHECK_CUDA(cudaEventElapsedTime(&p, h->c.ev_t[2], h->c.ev_t[3]));
+      ALM_CHECK_CUDA(cudaEventElapsedTime(&r, h->c.ev_t[3], h->c.ev_t[4]));
+    }
+    if (encode_ms) *encode_ms = e;
+    if (pt_ms) *pt_ms = p;
+    if (polyrec_ms) *polyrec_ms = r;
   });
 }
 

@@ -493,6 +493,7 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   auto kern = gemm_tcgen05_kernel<BLOCK_N, NSPLIT>;
   if (!attr_set) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    pin_carveout(kern);
     attr_set = true;
   }
   p.n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -514,7 +515,11 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   const CUtensorMap ta_hi = make_tmap(c, A.hi, A, a_rows, pa);
   const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N, pb);
   const CUtensorMap ta_lo = ta_hi, tb_lo = tb_hi;  // kept in the signature; the 5-D maps cover both planes
-  const int grid = static_cast<int>(std::min<long>(p.num_tiles, c->num_sms));
+  // Small launches (the per-token decode GEMMs) leave half of the SMs to the kernels of the other in-flight
+  // streams / batches: every CTA of this kernel needs a whole SM (231 KB of shared memory).
+  long cap = c->num_sms;
+  if (c->small_grid_cap > 0 && p.num_tiles <= 2L * c->num_sms) cap = c->small_grid_cap;
+  const int grid = static_cast<int>(std::min<long>(p.num_tiles, cap));
   kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
 

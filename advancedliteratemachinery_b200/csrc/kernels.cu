@@ -478,21 +478,42 @@ softmax_rows_kernel(const float* __restrict__ s, long lds, int n, const uint8_t*
 // ---------------------------------------------------------------------------------------------
 template <int MR, int NW>  // MR = row capacity (8/16/32), NW = K / 128 float4 slices of the weight row per lane
 __global__ void __launch_bounds__(128)
-gemv_rows_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ W, const float* __restrict__ bias,
-                 const float* __restrict__ resid, long ldr, float* __restrict__ out, long ldo, int M, int N, int K,
-                 int act) {
+gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int n_split, long ldx,
+                 const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ resid, long ldr,
+                 float* __restrict__ out, long ldo, int M, int N, int K, int act, int use_smem) {
+  extern __shared__ __align__(16) float sx[];  // [M][K] activation rows (when they fit)
   const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (n >= N) return;
   const int lane = threadIdx.x & 31;
+  const float* xin = (blockIdx.x * 4 < n_split) ? x : x2;  // columns [0, n_split) read x, the rest x2 (fused q|k|v)
   // the whole weight row of this column is requested up front (NW independent 16-byte loads per lane = one HBM
-  // round trip); the activation rows are then read from L1/L2
+  // round trip) ...
   float4 w[NW];
-  const float* wrow = W + static_cast<long>(n) * K;
+  if (n < N) {
+    const float* wrow = W + static_cast<long>(n) * K;
 #pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    const int k0 = (i * 32 + lane) * 4;
-    w[i] = k0 < K ? *reinterpret_cast<const float4*>(wrow + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NW; ++i) {
+      const int k0 = (i * 32 + lane) * 4;
+      w[i] = k0 < K ? *reinterpret_cast<const float4*>(wrow + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
+  // ... while the CTA stages the few activation rows in shared memory with cp.async: every 16-byte copy is in
+  // flight at once, so the staging costs one memory round trip however many rows there are
+  if (use_smem) {
+    const int k4 = K >> 2;
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sx));
+    for (int i = threadIdx.x; i < M * k4; i += 128) {
+      const int m = i / k4, c4 = i - m * k4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + static_cast<uint32_t>((m * K + c4 * 4) * 4)),
+                   "l"(xin + m * ldx + c4 * 4)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  if (n >= N) return;
+  const float* xs = use_smem ? sx : xin;
+  const long lds = use_smem ? K : ldx;
   float mine = 0.f;
 #pragma unroll
   for (int m = 0; m < MR; ++m) {
@@ -502,7 +523,7 @@ gemv_rows_kernel(const float* __restrict__ x, long ldx, const float* __restrict_
       for (int i = 0; i < NW; ++i) {
         const int k0 = (i * 32 + lane) * 4;
         if (k0 < K) {
-          const float4 a = *reinterpret_cast<const float4*>(x + m * ldx + k0);
+          const float4 a = *reinterpret_cast<const float4*>(xs + m * lds + k0);
           acc = fmaf(a.x, w[i].x, acc); acc = fmaf(a.y, w[i].y, acc);
           acc = fmaf(a.z, w[i].z, acc); acc = fmaf(a.w, w[i].w, acc);
         }
@@ -533,6 +554,7 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
   dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb)), block(wpb * 32);
 #define ALM_GLN(NVV)                                                                                              \
   case NVV:                                                                                                       \
+    ALM_PIN_CARVEOUT(gather_ln_kernel<NVV>);                                                                      \
     gather_ln_kernel<NVV><<<grid, block, 0, c->stream>>>(src, lds, map, nsrc, Cs, rows, gamma, beta, eps,         \
                                                          zero_missing ? 1 : 0, add, ld_add, out_f32, ldo_f32,     \
                                                          out_hi, out_lo, ldo_bf, out2_hi, out2_lo, out2_f32);     \
@@ -580,6 +602,7 @@ void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, 
 void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint8_t* kpm, int rows_per_mask,
                   long mask_ld, float* out_f32, bf16* out_hi, bf16* out_lo, long ldo) {
   if (rows == 0) return;
+  ALM_PIN_CARVEOUT(softmax_rows_kernel);
   softmax_rows_kernel<<<static_cast<unsigned>(rows), 128, 0, c->stream>>>(s, lds, n, kpm, rows_per_mask, mask_ld,
                                                                           out_f32, out_hi, out_lo, ldo);
   count_launch(c);
@@ -589,13 +612,26 @@ void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint
 }  // namespace alm
 
 namespace alm {
-void gemv_rows(Ctx* c, const float* x, long ldx, const float* W, const float* bias, const float* resid, long ldr,
-               float* out, long ldo, int M, int N, int K, int act) {
-  ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048, ALM_ERR_INVALID,
+void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, const float* W, const float* bias,
+               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act) {
+  ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048 && n_split % 4 == 0, ALM_ERR_INVALID,
               "gemv_rows: M <= 32, K % 4 == 0, K <= 2048");
   const unsigned grid = static_cast<unsigned>((N + 3) / 4);
-#define ALM_GEMV(MRV, NWV) \
-  gemv_rows_kernel<MRV, NWV><<<grid, 128, 0, c->stream>>>(x, ldx, W, bias, resid, ldr, out, ldo, M, N, K, act)
+  const size_t sm = static_cast<size_t>(M) * K * sizeof(float);
+  const int use_smem = sm <= 160 * 1024;
+  const size_t dyn = use_smem ? sm : 0;
+#define ALM_GEMV(MRV, NWV)                                                                                         \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      ALM_CHECK_CUDA(cudaFuncSetAttribute(gemv_rows_kernel<MRV, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          160 * 1024));                                                            \
+      alm::pin_carveout(gemv_rows_kernel<MRV, NWV>);                                                               \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    gemv_rows_kernel<MRV, NWV><<<grid, 128, dyn, c->stream>>>(x, x2 ? x2 : x, n_split, ldx, W, bias, resid, ldr,   \
+                                                              out, ldo, M, N, K, act, use_smem);                  \
+  } while (0)
   const int nw = K <= 512 ? 4 : 16;
   if (M <= 8) { if (nw == 4) ALM_GEMV(8, 4); else ALM_GEMV(8, 16); }
   else if (M <= 16) { if (nw == 4) ALM_GEMV(16, 4); else ALM_GEMV(16, 16); }

@@ -170,6 +170,12 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
       w.n1 = load_ln(c, t, p + "norm1", 512);
       w.n2 = load_ln(c, t, p + "norm2", 512);
       w.n3 = load_ln(c, t, p + "norm3", 512);
+      {
+        const HostTensor& ipw0 = need(t, p + "self_attn.in_proj_weight");
+        const HostTensor& ipb0 = need(t, p + "self_attn.in_proj_bias");
+        w.sa_qkv_f = upload_f32(c, ipw0.f32.data(), ipw0.numel());
+        w.sa_qkv_b = upload_f32(c, ipb0.f32.data(), ipb0.numel());
+      }
       w.sa_qk = load_inproj_rows(c, t, p + "self_attn", 0, 1024);
       w.sa_v = load_inproj_rows(c, t, p + "self_attn", 1024, 512);
       w.sa_out = load_lin(c, t, p + "self_attn.out_proj", 512, 512, true, 0, true);
@@ -208,6 +214,8 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   Arena& ws = c->ws;
   ws.off = 0;
   m->encoded = false;
+  if (!c->ev_t[0]) for (auto& e : c->ev_t) ALM_CHECK_CUDA(cudaEventCreate(&e));
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[0], c->stream));
   m->B = B; m->H = H; m->W = W;
   int hs = (H + 3) / 4, wsz = (W + 3) / 4;
   for (int s = 0; s < 4; ++s) {
@@ -352,6 +360,8 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   }
   ws.release(m->ws_mark);
   m->encoded = true;
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[1], c->stream));
+  c->timing_valid[0] = true;
 }
 
 // ================================================================================================ decode
@@ -364,6 +374,7 @@ struct DecodeBufs {
   int* tpos = nullptr;    // device-side position counter (so one captured graph serves every token)
   SplitBuf ln, lnp, att, q, o, hid, h0, h1;
   float *qk = nullptr, *v = nullptr, *scores = nullptr, *logits = nullptr, *qf = nullptr;
+  float* qkv = nullptr;  // skinny path: fused [S,1536] q|k|v
   float *lnf = nullptr, *lnpf = nullptr, *attf = nullptr, *of = nullptr, *hidf = nullptr, *h0f = nullptr, *h1f = nullptr;
   bool skinny = false;          // S <= 32 live sequences: all-fp32 SIMT GEMV path instead of tensor-core tiles
   float* xq_partial = nullptr;  // fused single-query cross-attention: split partials + counters
@@ -397,6 +408,7 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     d.lnf = c->ws.get<float>(S * 512); d.lnpf = c->ws.get<float>(S * 512); d.attf = c->ws.get<float>(S * 512);
     d.of = c->ws.get<float>(S * 512); d.hidf = c->ws.get<float>(S * 2048); d.h0f = c->ws.get<float>(S * 512);
     d.h1f = c->ws.get<float>(S * 512);
+    d.qkv = c->ws.get<float>(S * 1536);
   }
   if (Ncap == 1) {
     d.xq_splits = cross_attn_q1_splits(c, B, m->M);
@@ -427,16 +439,16 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     // One live sequence per image and at most 32 of them: every linear is a skinny fp32 GEMV (exact fp32 weights,
     // one warp per output column), no operand splitting, no tensor-core tile padding.
     auto lin = [&](const float* x, int K, const Lin& w, int act, float* out, const float* resid) {
-      gemv_rows(c, x, K, w.wf, w.b, resid, w.w.N, out, w.w.N, S, w.w.N, K, act);
+      gemv_rows(c, x, nullptr, 1 << 30, K, w.wf, w.b, resid, w.w.N, out, w.w.N, S, w.w.N, K, act);
     };
     for (int l = 0; l < 4; ++l) {
       const DecLayerW& w = m->dec[d][l];
       const long dl = static_cast<long>(d) * 4 + l;
       gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n1.g, w.n1.b, 1e-5f, false, qpos, 0, u.lnf, 512, nullptr, nullptr, 512,
                 nullptr, nullptr, u.lnpf);
-      lin(u.lnpf, 512, w.sa_qk, ACT_NONE, u.qk, nullptr);
-      lin(u.lnf, 512, w.sa_v, ACT_NONE, u.v, nullptr);
-      self_attn_step(c, u.qk, u.v, u.kc[l], u.vc[l], S, u.tpos, u.Tmax, nullptr, nullptr, u.attf);
+      // q|k from LN(x)+pos and v from LN(x) in ONE launch: the fp32 in_proj rows are contiguous (q, k, v)
+      gemv_rows(c, u.lnpf, u.lnf, 1024, 512, w.sa_qkv_f, w.sa_qkv_b, nullptr, 0, u.qkv, 1536, S, 1536, 512, ACT_NONE);
+      self_attn_step(c, u.qkv, u.qkv + 1024, u.kc[l], u.vc[l], S, u.tpos, u.Tmax, nullptr, nullptr, u.attf, 1536, 1536);
       lin(u.attf, 512, w.sa_out, ACT_NONE, u.x, u.x);
       gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n2.g, w.n2.b, 1e-5f, false, qpos, 0, nullptr, 512, nullptr, nullptr, 512,
                 nullptr, nullptr, u.lnpf);
@@ -606,6 +618,8 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   Arena& ws = c->ws;
   ws.release(m->ws_mark);
   HeadCfg hc{cfg.num_bins, cfg.pt_eos, cfg.rec_eos, cfg.recog_pad, m->vie};
+  c->timing_valid[1] = false;
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[2], c->stream));
 
   // ------------------------------------------------------------------ pt loop (transformer.py:102-141)
   const int Tpt = n_prompt + cfg.pt_seq_length;
@@ -644,6 +658,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
       }
     }
   }
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[3], c->stream));
   std::vector<int> h_ntok(B), h_tok(static_cast<size_t>(B) * Tpt);
   std::vector<float> h_prob(static_cast<size_t>(B) * cfg.pt_seq_length);
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_ntok.data(), ntok, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -740,6 +755,8 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   c->stream = s0;
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_join, s1));
   ALM_CHECK_CUDA(cudaStreamWaitEvent(s0, c->ev_join, 0));
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[4], s0));
+  c->timing_valid[1] = true;
   for (int phase = 1; phase <= 2; ++phase) {
     const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
     const int T = 3 + len;

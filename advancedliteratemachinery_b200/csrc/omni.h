@@ -33,6 +33,8 @@ struct DecLayerW {
   LNW n1, n2, n3;
   Lin sa_qk;   // rows [0,1024) of self_attn.in_proj (q then k)
   Lin sa_v;    // rows [1024,1536)
+  float* sa_qkv_f = nullptr;  // exact fp32 packed in_proj [1536,512] + bias [1536] (skinny decode path)
+  float* sa_qkv_b = nullptr;
   Lin sa_out;
   Lin ca_q;    // rows [0,512) of multihead_attn.in_proj
   Lin ca_out;
@@ -98,7 +100,7 @@ void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, co
 void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, const float* word_emb,
               const float* pos_emb, const float* gamma, const float* beta, float* x, float* qpos);
 void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* tptr, int Tmax,
-                    bf16* out_hi, bf16* out_lo, float* out_f32 = nullptr);
+                    bf16* out_hi, bf16* out_lo, float* out_f32 = nullptr, int ld_qk = 1024, int ld_v = 512);
 void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
                  int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image);

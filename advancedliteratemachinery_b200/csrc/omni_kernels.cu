@@ -228,7 +228,7 @@ embed_ln_kernel(const int* __restrict__ tokens, int tstride, const int* __restri
 __global__ void __launch_bounds__(128)
 self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vnew, float* __restrict__ kc,
                       float* __restrict__ vc, int S, const int* __restrict__ tptr, int Tmax, bf16* __restrict__ out_hi,
-                      bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
+                      bf16* __restrict__ out_lo, float* __restrict__ out_f32, int ld_qk, int ld_v) {
   extern __shared__ float sp[];  // [4 warps][Tmax]
   const int t = *tptr;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -238,11 +238,11 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
   float* p = sp + wid * Tmax;
   float* krow = kc + (static_cast<long>(s) * Tmax + t) * 512 + h * 64;
   float* vrow = vc + (static_cast<long>(s) * Tmax + t) * 512 + h * 64;
-  const float* qrow = qk + static_cast<long>(s) * 1024 + h * 64;
+  const float* qrow = qk + static_cast<long>(s) * ld_qk + h * 64;
   // append
   krow[lane] = qrow[512 + lane]; krow[lane + 32] = qrow[512 + lane + 32];
-  vrow[lane] = vnew[static_cast<long>(s) * 512 + h * 64 + lane];
-  vrow[lane + 32] = vnew[static_cast<long>(s) * 512 + h * 64 + lane + 32];
+  vrow[lane] = vnew[static_cast<long>(s) * ld_v + h * 64 + lane];
+  vrow[lane + 32] = vnew[static_cast<long>(s) * ld_v + h * 64 + lane + 32];
   __syncwarp();
   float q[64];
 #pragma unroll
@@ -330,7 +330,7 @@ cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi
 #pragma unroll
     for (int e = 0; e < 8; ++e) qd[e] = sq[8 * sub + e];
     const long kbase = ((static_cast<long>(img) * 96 + h) * M + k0) * 64 + 8 * sub;  // K_c[img][dl(base)][h][key][64]
-#pragma unroll 4
+#pragma unroll 8
     for (int kb = wid * 4; kb < nk; kb += (XQ_THREADS / 32) * 4) {  // warp-uniform trip count (shuffles inside)
       const int kk = kb + kq;
       const bool live = kk < nk;
@@ -379,24 +379,34 @@ cross_attn_q1_kernel(const float* __restrict__ q, const bf16* __restrict__ kc_hi
     const int nk8 = (nk + 7) >> 3;  // groups of 8 keys (p = 0 beyond nk)
     for (int kk = nk + t; kk < nk8 * 8; kk += XQ_THREADS) xs[kk] = 0.f;
     __syncthreads();
-#pragma unroll 2
-    for (int dd = 0; dd < 8; ++dd) {
-      const int dim = wid * 8 + dd;
-      const long vrow = (static_cast<long>(img) * 6144 + h * 64 + dim) * Mpad + k0;
-      float acc = 0.f;
-#pragma unroll 2
-      for (int gidx = lane; gidx < nk8; gidx += 32) {
-        const uint4 vh = *reinterpret_cast<const uint4*>(vt_hi + vrow + 8 * gidx);
-        const uint4 vl = *reinterpret_cast<const uint4*>(vt_lo + vrow + 8 * gidx);
-        const float4 p0 = *reinterpret_cast<const float4*>(xs + 8 * gidx);
-        const float4 p1 = *reinterpret_cast<const float4*>(xs + 8 * gidx + 4);
-        float vf[8];
-        bf16x8_to_f32(vh, vl, vf);
-        acc = fmaf(p0.x, vf[0], acc); acc = fmaf(p0.y, vf[1], acc); acc = fmaf(p0.z, vf[2], acc); acc = fmaf(p0.w, vf[3], acc);
-        acc = fmaf(p1.x, vf[4], acc); acc = fmaf(p1.y, vf[5], acc); acc = fmaf(p1.z, vf[6], acc); acc = fmaf(p1.w, vf[7], acc);
+    float acc8[8];
+#pragma unroll
+    for (int dd = 0; dd < 8; ++dd) acc8[dd] = 0.f;
+    const long vrow0 = (static_cast<long>(img) * 6144 + h * 64 + wid * 8) * Mpad + k0;
+    for (int gidx = lane; gidx < nk8; gidx += 32) {
+      // all 16 vector loads of this step (8 dims x hi/lo) are issued before any is consumed
+      uint4 vh[8], vl[8];
+#pragma unroll
+      for (int dd = 0; dd < 8; ++dd) {
+        vh[dd] = *reinterpret_cast<const uint4*>(vt_hi + vrow0 + static_cast<long>(dd) * Mpad + 8 * gidx);
+        vl[dd] = *reinterpret_cast<const uint4*>(vt_lo + vrow0 + static_cast<long>(dd) * Mpad + 8 * gidx);
       }
-      acc = warp_sum(acc);
-      if (lane == 0) so[dim] = acc;
+      const float4 p0 = *reinterpret_cast<const float4*>(xs + 8 * gidx);
+      const float4 p1 = *reinterpret_cast<const float4*>(xs + 8 * gidx + 4);
+#pragma unroll
+      for (int dd = 0; dd < 8; ++dd) {
+        float vf[8];
+        bf16x8_to_f32(vh[dd], vl[dd], vf);
+        float a = acc8[dd];
+        a = fmaf(p0.x, vf[0], a); a = fmaf(p0.y, vf[1], a); a = fmaf(p0.z, vf[2], a); a = fmaf(p0.w, vf[3], a);
+        a = fmaf(p1.x, vf[4], a); a = fmaf(p1.y, vf[5], a); a = fmaf(p1.z, vf[6], a); a = fmaf(p1.w, vf[7], a);
+        acc8[dd] = a;
+      }
+    }
+#pragma unroll
+    for (int dd = 0; dd < 8; ++dd) {
+      const float a = warp_sum(acc8[dd]);
+      if (lane == 0) so[wid * 8 + dd] = a;
     }
     __syncthreads();
   }
@@ -587,20 +597,23 @@ void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, co
 }
 void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, const float* word_emb,
               const float* pos_emb, const float* gamma, const float* beta, float* x, float* qpos) {
+  ALM_PIN_CARVEOUT(embed_ln_kernel);
   embed_ln_kernel<<<(S + 7) / 8, 256, 0, c->stream>>>(tokens, tstride, tptr, S, word_emb, pos_emb, gamma, beta, x, qpos);
   count_launch(c); check_launch("embed_ln");
 }
 void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* t, int Tmax,
-                    bf16* out_hi, bf16* out_lo, float* out_f32) {
+                    bf16* out_hi, bf16* out_lo, float* out_f32, int ld_qk, int ld_v) {
   const long groups = static_cast<long>(S) * 8;
   const size_t sm = static_cast<size_t>(4) * Tmax * sizeof(float);
+  ALM_PIN_CARVEOUT(self_attn_step_kernel);
   self_attn_step_kernel<<<static_cast<unsigned>((groups + 3) / 4), 128, sm, c->stream>>>(qk, vnew, kc, vc, S, t, Tmax,
-                                                                                        out_hi, out_lo, out_f32);
+                                                                                        out_hi, out_lo, out_f32, ld_qk, ld_v);
   count_launch(c); check_launch("self_attn_step");
 }
 void head_select(Ctx* c, const float* logits, int S, int V, int nsoft, int phase, const HeadCfg& cfg, int* tokens,
                  int tstride, const int* tptr, int n_prompt_m1, float* probs, int pstride, int* finished, int* ntok,
                  int seqs_per_image) {
+  ALM_PIN_CARVEOUT(head_select_kernel);
   head_select_kernel<<<S, 256, 0, c->stream>>>(logits, V, nsoft, phase, cfg, tokens, tstride, tptr, n_prompt_m1, probs,
                                                pstride, finished, ntok, seqs_per_image);
   count_launch(c); check_launch("head_select");
@@ -621,6 +634,7 @@ void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo,
   static bool attr = false;
   if (!attr) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    pin_carveout(cross_attn_q1_kernel);
     attr = true;
   }
   dim3 grid(nimg * 8, nsplit);
@@ -635,6 +649,7 @@ int cross_attn_q1_splits(Ctx* c, int nimg, int M) {
   return ns;
 }
 void add_i32(Ctx* c, int* p, int v) {
+  ALM_PIN_CARVEOUT(add_i32_kernel);
   add_i32_kernel<<<1, 1, 0, c->stream>>>(p, v);
   count_launch(c); check_launch("add_i32");
 }

@@ -167,6 +167,9 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--nsplit', type=int, default=3, help='3 = fp32-class split operands (parity mode), 1 = bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--grid-cap', type=int, default=0)
+    ap.add_argument('--inflight', type=int, default=3, help='independent batches in flight per GPU (one context + stream '
+                    'each); the per-token decode loops are latency-bound, so concurrent batches fill the idle SMs')
     ap.add_argument('--cpu-sample', nargs=2, type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_sample:
@@ -194,12 +197,20 @@ def main():
     sd = W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0) if rank == 0 else None
     if world > 1:
         sd = broadcast_state_dict(sd, src=0, device=torch.device('cuda', local))
-    stream = torch.cuda.Stream()
     vocab = OmniVocab(pt_seq_length=2 * N_INST, rec_length=REC_LEN)
-    ctx = _lib.Context(local, stream.cuda_stream)
-    ctx.set_option('nsplit', args.nsplit)
-    model = OmniParserB200(sd, vocab, ctx=ctx)
+    C_ = max(1, args.inflight)
+    streams = [torch.cuda.Stream() for _ in range(C_)]
+    ctxs, models = [], []
+    for j in range(C_):
+        cx = _lib.Context(local, streams[j].cuda_stream)
+        cx.set_option('nsplit', args.nsplit)
+        cx.set_option('workspace_mb', 20480)
+        if args.grid_cap:
+            cx.set_option('small_grid_cap', args.grid_cap)
+        ctxs.append(cx)
+        models.append(OmniParserB200(sd, vocab, ctx=cx))
     del sd
+    stream, ctx, model = streams[0], ctxs[0], models[0]
 
     B = args.batch
     g = torch.Generator().manual_seed(1000 + rank * B)
@@ -207,36 +218,56 @@ def main():
     dev_pages = host_pages.cuda(non_blocking=False)
     h2d_bytes = host_pages.numel() * 4
 
-    def step_resident():
-        model.encode(dev_pages, None)
-        return model.decode()
+    def step_resident(j=0):
+        models[j].encode(dev_pages, None)
+        return models[j].decode()
 
-    def step_e2e():
-        return model.forward_batch(NestedTensor(host_pages, None))
+    def step_e2e(j=0):
+        return models[j].forward_batch(NestedTensor(host_pages, None))
+
+    def run_steps(fn, steps):
+        """`steps` batches, round-robin over the in-flight contexts (one host thread per context: the C calls
+        release the GIL, the per-context streams overlap on the device)."""
+        outs = [None] * C_
+        if C_ == 1:
+            for _ in range(steps):
+                outs[0] = fn(0)
+            return outs[0]
+        def worker(j):
+            for _ in range(j, steps, C_):
+                outs[j] = fn(j)
+        ts = [threading.Thread(target=worker, args=(j,)) for j in range(C_)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return next(o for o in outs if o is not None)
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+        run_steps(fn, max(warmup, C_))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ctx.launch_count(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                outs = fn()
-            e1.record(stream)
+        for cx in ctxs:
+            cx.launch_count(True)
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(C_)]
+        e0.record(streams[0])
+        for j in range(1, C_):
+            streams[j].wait_event(e0)
+        outs = run_steps(fn, steps)
+        for j in range(C_):
+            ends[j].record(streams[j])
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = max(e0.elapsed_time(e1), 0.0)
+        ms = max(e0.elapsed_time(e) for e in ends)
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), ctx.launch_count(True), outs
+        return float(t.item()), sum(cx.launch_count(True) for cx in ctxs), outs
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -257,6 +288,9 @@ def main():
     gemm_ms = ctx.bench_gemm(M_, N_, K_, 20)
     burst, sustained, hbm, peak_src = peaks()
     achieved = 2.0 * M_ * N_ * K_ / (gemm_ms * 1e-3) / 1e12
+    torch.cuda.synchronize()
+    step_resident(0)                       # one isolated step: per-phase device times without cross-batch contention
+    phase_ms = ctx.omni_last_timing()
     ctx.set_option('profile_gemm', 1)
     step_resident()
     g_ms, g_flops, g_n = ctx.profile_read()
@@ -284,10 +318,11 @@ def main():
         'data': 'synthetic',
         'config': {'workload': f'OmniParser Swin-B text spotting, {PAGE}x{PAGE} synthetic pages, batch {B} per GPU, '
                                f'N={N_INST} instances/page pinned (pt 128 + poly 32 + rec {REC_LEN} tokens)',
-                   'global_batch': world * B, 'parallelism': f'dp{world}', 'l2': 'inputs (201 MB/step) and activations '
+                   'global_batch': world * B, 'parallelism': f'dp{world}', 'in_flight_batches_per_gpu': C_, 'l2': 'inputs (201 MB/step) and activations '
                    'exceed the 126 MB L2; no explicit flush', 'weights': 'synthetic seed 0 (oracle/weights.py), pt_eos pinned'},
         'decoded_chars_per_sec': world * n_chars / (ms_per_step * 1e-3),
         'encoder_ms_per_batch': enc_ms,
+        'phase_ms': phase_ms,
         'encoder_algorithmic_tflops': ENC_GFLOP_PER_IMAGE * B / enc_ms,
         'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
         'gpu_launches': launches,

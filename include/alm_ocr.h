@@ -80,6 +80,8 @@ ALM_API const char* alm_version(void);
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
  *          "trace_gemm" (capacity; see alm_trace_read), "trace_detail" (see alm_bench_gemm_ex),
  *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
+ *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
+ *          streams / in-flight batches can share the GPU),
  *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
  *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
@@ -98,6 +100,8 @@ ALM_API int alm_trace_read(alm_ctx* ctx, unsigned long long* out, int max_record
 /* Times `iters` back-to-back launches of one [M,K]x[N,K]^T GEMM (operands pre-split, resident) with CUDA events
  * on the context stream; ms_per_launch is the average kernel duration. */
 ALM_API int alm_bench_gemm(alm_ctx* ctx, int M, int N, int K, int iters, float* ms_per_launch);
+/* Replay cost (microseconds per node) of a captured chain of `nodes` trivial dependent kernels. */
+ALM_API int alm_bench_graph_floor(alm_ctx* ctx, int nodes, int iters, float* us_per_node);
 /* Same, batched, with a choice of epilogue (split_out: bf16 hi/lo output; act: 0/1/2).  With the "trace_detail" option
  * on, detail_out receives 64 x 6 u64 stamps of CTA 0's first tiles: TMA issue, MMA tile start, operands landed,
  * MMA committed, epilogue start, epilogue end (ns, %globaltimer). */
@@ -163,6 +167,9 @@ ALM_API int alm_omni_decode_kie(alm_ctx* ctx, const int64_t* pt_prompt, int n_pr
  * kind: 0 = pt, 1 = poly, 2 = rec. */
 ALM_API int alm_omni_decode_logits(alm_ctx* ctx, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits);
 ALM_API int alm_omni_vocab(alm_ctx* ctx);
+/* Device time (CUDA events on the context stream) of the last alm_omni_encode and of the two halves of the last
+ * decode: the point loop, and the polygon + recognition loops (incl. the host round trip between them); -1 = n/a. */
+ALM_API int alm_omni_last_timing(alm_ctx* ctx, float* encode_ms, float* pt_ms, float* polyrec_ms);
 
 /* ---- MGP-STR ------------------------------------------------------------------------------- */
 /* Replaces `model(image, is_eval=True)` (OCR/MGP-STR/modules/mgp_str.py:96-101).
