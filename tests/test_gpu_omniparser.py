@@ -333,3 +333,19 @@ def test_kie_decode_matches_reference_fixture(golden_dir):
     assert np.array_equal(raw['tokens'][0, :raw['n_tok'][0]], gold['pt_seq'])
     np.testing.assert_allclose(raw['probs'][0, :raw['n_tok'][0]], gold['pt_probs'][:raw['n_tok'][0]], rtol=2e-3)
     m.ctx.close()
+
+
+def test_full_size_page_encoder_matches_oracle():
+    """BASELINE config-2 geometry (1024x1024: every Swin stage zero-padded to x7, 4096 memory tokens): the
+    encoder + FPN + input_proj output of one page against the CPU oracle."""
+    from oracle import omniparser_ref as O
+    from tests.conftest import omni_sd
+    sd = omni_sd(0, 0.45)
+    m = model_for(0, 0.45)
+    g = torch.Generator().manual_seed(1000)
+    img = torch.randn(1, 3, 1024, 1024, generator=g)
+    mask = torch.zeros(1, 1024, 1024, dtype=torch.bool)
+    mem, pos, kpm, hw = O.encode(img, mask, sd)
+    assert m.encode(img.cuda(), None) == (1, 64, 64) and hw == (64, 64)
+    assert _rel(m.memory(0), mem) < 1e-4
+    assert float((m.memory(1) - pos).abs().max()) < 5e-6
