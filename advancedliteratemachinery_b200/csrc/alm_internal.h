@@ -164,6 +164,7 @@ struct Ctx {
   int* trace_idx = nullptr;
   int trace_cap = 0;
   unsigned long long* detail_buf = nullptr;  // [64][6] per-role stamps of CTA 0, overwritten by every GEMM (debug)
+  int xattn_impl = 0;  // 0 = fused flash-style multi-query cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
@@ -203,6 +204,11 @@ void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp
 
 void window_attention(Ctx* c, const float* qkv, int C, int heads, int nWh, int nWw, int B, int shift, int Hp, int Wp,
                       const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
+
+// same, from the split-bf16 qkv planes the GEMM epilogue writes (q rows pre-scaled by WATTN_QSCALE at load time)
+constexpr float WATTN_QSCALE = 0.17677669529663687f;  // 32 ** -0.5 (swin_transformer.py:130)
+void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B,
+                            int shift, int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
 
 void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo);
 

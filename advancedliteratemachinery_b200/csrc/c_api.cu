@@ -176,6 +176,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
         ALM_CHECK_CUDA(cudaMalloc(&h->c.detail_buf, 64 * 6 * sizeof(unsigned long long)));
         ALM_CHECK_CUDA(cudaMemset(h->c.detail_buf, 0, 64 * 6 * sizeof(unsigned long long)));
       }
+    } else if (k == "xattn_impl") {
+      h->c.xattn_impl = value ? 1 : 0;
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
     } else if (k == "small_grid_cap") {

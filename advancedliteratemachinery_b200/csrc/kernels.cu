@@ -1,7 +1,7 @@
 // Non-GEMM kernels of the encoder path: patch im2col, gather + LayerNorm + operand split, Swin window
 // attention core, row softmax.  All are HBM-/latency-bound: vectorised 16-byte accesses, one warp per row.
 #include "alm_internal.h"
-#include "ptx.cuh"
+#include "mma.cuh"
 
 namespace alm {
 
@@ -230,69 +230,37 @@ window_attention_kernel(const float* __restrict__ qkv, int C, int nWh, int nWw, 
 
 // ---------------------------------------------------------------------------------------------
 // Swin W-MSA core on the tensor cores: one CTA (4 warps) per (window, head); warp w owns query rows 16w..16w+15.
-// q*scale, k, v are split into bf16 (hi, lo) pairs while being staged into shared memory, and both products
+// Input is the qkv projection as split-bf16 planes straight from the GEMM epilogue (q already carries the
+// 32^-0.5 scale: it is folded into the q rows of the qkv weight at load time), so staging is pure cp.async --
+// no conversion, no transposition (P.V reads v [key][dim] through ldmatrix.trans).  Both products
 // (S = q k^T, 64x64x32 ; O = P v, 64x32x64, padded from 49) run as mma.sync.m16n8k16 with the three-term split
 // hi*hi + lo*hi + hi*lo accumulated in fp32 registers -- the same fp32-class scheme as the GEMM engine.
 // Softmax stays in fp32 registers (quad shuffles).  These 49x49x32 tiles are too small for a tcgen05
 // 128-row instruction (7 % of Swin FLOPs), so the warp-level MMA is the right granularity.
 // ---------------------------------------------------------------------------------------------
-constexpr int QK_PITCH = 40;   // bf16 per row of the q / k tiles (32 + 8 pad -> conflict-free fragment loads)
-constexpr int VT_PITCH = 72;   // bf16 per row of the transposed v tile [dim][key] (64 + 8 pad)
-
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  bf16 hx, lx, hy, ly;
-  split_bf16(x, hx, lx);
-  split_bf16(y, hy, ly);
-  hi = pack_bf16(hx, hy);
-  lo = pack_bf16(lx, ly);
-}
+constexpr int WS_PITCH = 40;   // bf16 per staged row (32 + 8 pad -> conflict-free ldmatrix)
+constexpr int WS_TILE = 64 * WS_PITCH;
 
 __global__ void __launch_bounds__(128)
-window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int nWw, int shift, int Hp, int Wp,
-                            const float* __restrict__ bias_dense, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
-                            float* __restrict__ out_f32) {
-  __shared__ __align__(16) bf16 sq[2][64 * QK_PITCH];   // [hi/lo][row][dim]
-  __shared__ __align__(16) bf16 sk[2][64 * QK_PITCH];
-  __shared__ __align__(16) bf16 svt[2][32 * VT_PITCH];  // [hi/lo][dim][key]
+window_attention_split_kernel(const bf16* __restrict__ qkv_hi, const bf16* __restrict__ qkv_lo, int C, int nWh, int nWw,
+                              int shift, int Hp, int Wp, const float* __restrict__ bias_dense, bf16* __restrict__ out_hi,
+                              bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
+  __shared__ __align__(16) bf16 st[2][3][WS_TILE];  // [hi/lo][q,k,v][row][dim]
   __shared__ int sreg[64];
   const int win = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const long row0 = static_cast<long>(win) * WT;
-  const int ld = 3 * C;
-  const float scale = 0.17677669529663687f;  // 32 ** -0.5, applied to q before the product (swin_transformer.py:130)
-  // ---- stage q*scale, k, v^T (rows >= 49 zero)
-  for (int i = tid; i < 64 * 8; i += 128) {
-    const int r = i >> 3, c4 = (i & 7) * 4;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
-    if (r < WT) {
-      const float* base = qkv + (row0 + r) * ld + h * HD + c4;
-      q = *reinterpret_cast<const float4*>(base);
-      k = *reinterpret_cast<const float4*>(base + C);
-      v = *reinterpret_cast<const float4*>(base + 2 * C);
-      q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
-    }
-    uint32_t h0, l0, h1, l1;
-    split_pack2(q.x, q.y, h0, l0); split_pack2(q.z, q.w, h1, l1);
-    *reinterpret_cast<uint2*>(&sq[0][r * QK_PITCH + c4]) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(&sq[1][r * QK_PITCH + c4]) = make_uint2(l0, l1);
-    split_pack2(k.x, k.y, h0, l0); split_pack2(k.z, k.w, h1, l1);
-    *reinterpret_cast<uint2*>(&sk[0][r * QK_PITCH + c4]) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(&sk[1][r * QK_PITCH + c4]) = make_uint2(l0, l1);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
+  const long ld = 3L * C;
+  // ---- stage q, k, v (rows >= 49 zero-filled): 64 rows x 4 x 16-byte chunks per tile and plane
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      bf16 hh, ll;
-      split_bf16(vv[e], hh, ll);
-      svt[0][(c4 + e) * VT_PITCH + r] = hh;
-      svt[1][(c4 + e) * VT_PITCH + r] = ll;
-    }
+  for (int i = tid; i < 3 * 256; i += 128) {
+    const int which = i >> 8, rem = i & 255, r = rem >> 2, ch = (rem & 3) * 8;
+    const bool ok = r < WT;
+    const long src = (row0 + (ok ? r : 0)) * ld + which * C + h * HD + ch;
+    cp_async16(&st[0][which][r * WS_PITCH + ch], qkv_hi + src, ok ? 16 : 0);
+    cp_async16(&st[1][which][r * WS_PITCH + ch], qkv_lo + src, ok ? 16 : 0);
   }
+  cp_async_commit();
   if (tid < 64) {
     int reg = 0;
     if (shift > 0 && tid < WT) {
@@ -304,39 +272,34 @@ window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int n
     }
     sreg[tid] = reg;
   }
+  cp_async_wait<0>();
   __syncthreads();
 
   const int r_lo = warp * 16 + g, r_hi = r_lo + 8;  // the two query rows this lane holds
-  // ---- S = (q*scale) k^T : A fragments of q (hi, lo) for both k-steps
+  const int lrow = lane & 7, lmat = lane >> 3;
+  // ---- S = q k^T : A fragments of q (hi, lo) for both k-steps
   uint32_t aq[2][2][4];
 #pragma unroll
   for (int p = 0; p < 2; ++p)
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const bf16* b = &sq[p][ks * 16 + 2 * t];
-      aq[p][ks][0] = *reinterpret_cast<const uint32_t*>(b + r_lo * QK_PITCH);
-      aq[p][ks][1] = *reinterpret_cast<const uint32_t*>(b + r_hi * QK_PITCH);
-      aq[p][ks][2] = *reinterpret_cast<const uint32_t*>(b + r_lo * QK_PITCH + 8);
-      aq[p][ks][3] = *reinterpret_cast<const uint32_t*>(b + r_hi * QK_PITCH + 8);
-    }
+    for (int ks = 0; ks < 2; ++ks)
+      ldmatrix_x4(aq[p][ks], &st[p][0][(warp * 16 + (lane & 15)) * WS_PITCH + ks * 16 + (lane >> 4) * 8]);
   float s[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    uint32_t bh[4], bl[4];  // (ks0 b0, ks0 b1, ks1 b0, ks1 b1)
+    ldmatrix_x4(bh, &st[0][1][(8 * j + lrow) * WS_PITCH + lmat * 8]);
+    ldmatrix_x4(bl, &st[1][1][(8 * j + lrow) * WS_PITCH + lmat * 8]);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      const int off = (8 * j + g) * QK_PITCH + ks * 16 + 2 * t;
-      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sk[0][off]);
-      const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sk[0][off + 8]);
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sk[1][off]);
-      const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sk[1][off + 8]);
-      mma_bf16_16816(s[j], aq[0][ks], bh0, bh1);
-      mma_bf16_16816(s[j], aq[1][ks], bh0, bh1);
-      mma_bf16_16816(s[j], aq[0][ks], bl0, bl1);
+      mma_bf16_16816(s[j], aq[0][ks], bh[2 * ks], bh[2 * ks + 1]);
+      mma_bf16_16816(s[j], aq[1][ks], bh[2 * ks], bh[2 * ks + 1]);
+      mma_bf16_16816(s[j], aq[0][ks], bl[2 * ks], bl[2 * ks + 1]);
     }
   }
   // ---- + relative-position bias + shift mask; exclude MMA padding columns; softmax per row (fp32)
-  const float* bh = bias_dense + static_cast<long>(h) * WT * WT;
+  const float* bh_ = bias_dense + static_cast<long>(h) * WT * WT;
   const int reg_lo = sreg[min(r_lo, 63)], reg_hi = sreg[min(r_hi, 63)];
   float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
@@ -346,8 +309,8 @@ window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int n
       const int col = 8 * j + 2 * t + e;
       if (col < WT) {
         const int rc = sreg[col];
-        if (r_lo < WT) s[j][e] += __ldg(bh + r_lo * WT + col) + ((shift > 0 && rc != reg_lo) ? -100.0f : 0.0f);
-        if (r_hi < WT) s[j][2 + e] += __ldg(bh + r_hi * WT + col) + ((shift > 0 && rc != reg_hi) ? -100.0f : 0.0f);
+        if (r_lo < WT) s[j][e] += __ldg(bh_ + r_lo * WT + col) + ((shift > 0 && rc != reg_lo) ? -100.0f : 0.0f);
+        if (r_hi < WT) s[j][2 + e] += __ldg(bh_ + r_hi * WT + col) + ((shift > 0 && rc != reg_hi) ? -100.0f : 0.0f);
       } else {
         s[j][e] = -INFINITY;
         s[j][2 + e] = -INFINITY;
@@ -370,7 +333,8 @@ window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int n
     }
   sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1); sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
   sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1); sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
-  // ---- O = P v : P (normalised, split) becomes the A operand straight from the accumulator fragments
+  // ---- O = P v : P (normalised, split) becomes the A operand straight from the accumulator fragments;
+  //      v [key][dim] is read through ldmatrix.trans: matrix i = (key half i&1, dim tile 2*np + (i>>1))
   float o[4][4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
@@ -382,20 +346,22 @@ window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int n
     split_pack2(s[2 * kk + 1][0] / sum_lo, s[2 * kk + 1][1] / sum_lo, ph[2], pl[2]);
     split_pack2(s[2 * kk + 1][2] / sum_hi, s[2 * kk + 1][3] / sum_hi, ph[3], pl[3]);
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const int off = (8 * n + g) * VT_PITCH + kk * 16 + 2 * t;
-      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&svt[0][off]);
-      const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&svt[0][off + 8]);
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&svt[1][off]);
-      const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&svt[1][off + 8]);
-      mma_bf16_16816(o[n], ph, bh0, bh1);
-      mma_bf16_16816(o[n], pl, bh0, bh1);
-      mma_bf16_16816(o[n], ph, bl0, bl1);
+    for (int np = 0; np < 2; ++np) {
+      uint32_t vh[4], vl[4];  // (b0, b1) of dim tile 2np, (b0, b1) of dim tile 2np+1
+      const int off = (16 * kk + (lmat & 1) * 8 + lrow) * WS_PITCH + (2 * np + (lmat >> 1)) * 8;
+      ldmatrix_x4_trans(vh, &st[0][2][off]);
+      ldmatrix_x4_trans(vl, &st[1][2][off]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        mma_bf16_16816(o[2 * np + q], ph, vh[2 * q], vh[2 * q + 1]);
+        mma_bf16_16816(o[2 * np + q], pl, vh[2 * q], vh[2 * q + 1]);
+        mma_bf16_16816(o[2 * np + q], ph, vl[2 * q], vl[2 * q + 1]);
+      }
     }
   }
-  // ---- store: stage the 64x32 tile in smem (reusing the q buffers), then 16-byte row segments
+  // ---- store: stage the 64x32 tile in smem (reusing the q tiles), then 16-byte row segments
   __syncthreads();
-  float* so = reinterpret_cast<float*>(&sq[0][0]);  // 64 x 36 floats = 9216 B <= sizeof(sq) (10240 B)
+  float* so = reinterpret_cast<float*>(&st[0][0][0]);  // 64 x 36 floats = 9216 B <= 2 tiles (10240 B)
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
     *reinterpret_cast<float2*>(so + r_lo * 36 + 8 * n + 2 * t) = make_float2(o[n][0], o[n][1]);
@@ -409,6 +375,20 @@ window_attention_mma_kernel(const float* __restrict__ qkv, int C, int nWh, int n
     if (out_hi) store_split4(out_hi, out_lo, ooff, y);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + ooff) = y;
   }
+}
+
+// fp32 qkv -> split planes with the q columns scaled (only the op-level C entry point needs this: inside the
+// encoder the qkv GEMM epilogue writes the planes directly)
+__global__ void qkv_split_scale_kernel(const float* __restrict__ src, long rows, int C, float scale, bf16* __restrict__ hi,
+                                       bf16* __restrict__ lo) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c4 = (3 * C) >> 2;
+  if (i >= rows * c4) return;
+  const long r = i / c4;
+  const int e = static_cast<int>(i % c4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(src + r * 3 * C + e);
+  if (e < C) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+  store_split4(hi, lo, r * 3 * C + e, v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -576,18 +556,39 @@ void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp
   check_launch("im2col_patch4");
 }
 
+void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B,
+                            int shift, int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32) {
+  ALM_REQUIRE(C == heads * HD, ALM_ERR_UNSUPPORTED, "window_attention: head_dim must be 32");
+  dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
+  window_attention_split_kernel<<<grid, 128, 0, c->stream>>>(qkv_hi, qkv_lo, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi,
+                                                             out_lo, out_f32);
+  count_launch(c);
+  check_launch("window_attention_split");
+}
+
+// fp32 qkv (unscaled q) entry point of the op-level C API: wattn_impl 1 = fp32 SIMT kernel, 0 = the encoder's
+// tensor-core kernel behind a split + scale pass
 void window_attention(Ctx* c, const float* qkv, int C, int heads, int nWh, int nWw, int B, int shift, int Hp, int Wp,
                       const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32) {
   ALM_REQUIRE(C == heads * HD, ALM_ERR_UNSUPPORTED, "window_attention: head_dim must be 32");
-  dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
-  if (c->wattn_impl == 1)
+  if (c->wattn_impl == 1) {
+    dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
     window_attention_kernel<<<grid, 64, 0, c->stream>>>(qkv, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi, out_lo,
                                                         out_f32);
-  else
-    window_attention_mma_kernel<<<grid, 128, 0, c->stream>>>(qkv, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi,
-                                                             out_lo, out_f32);
+    count_launch(c);
+    check_launch("window_attention");
+    return;
+  }
+  const long rows = static_cast<long>(B) * nWh * nWw * WT;
+  const size_t mk = c->ws.mark();
+  bf16* hi = c->ws.get<bf16>(rows * 3 * C);
+  bf16* lo = c->ws.get<bf16>(rows * 3 * C);
+  const long total = rows * (3 * C / 4);
+  qkv_split_scale_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, c->stream>>>(qkv, rows, C, WATTN_QSCALE, hi, lo);
   count_launch(c);
-  check_launch("window_attention");
+  check_launch("qkv_split_scale");
+  window_attention_split(c, hi, lo, C, heads, nWh, nWw, B, shift, Hp, Wp, bias_dense, out_hi, out_lo, out_f32);
+  c->ws.release(mk);  // stream-ordered: later allocations are only touched by later launches
 }
 
 void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo) {

@@ -1,0 +1,49 @@
+// Warp-level tensor-core helpers (mma.sync.m16n8k16 bf16, ldmatrix, cp.async) shared by the attention kernels
+// whose tiles are too small for a 128-row tcgen05 instruction.
+#pragma once
+#include "ptx.cuh"
+
+namespace alm {
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// (x, y) -> packed bf16x2 hi and lo words with hi + lo == value to ~2^-17
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 hx, lx, hy, ly;
+  split_bf16(x, hx, lx);
+  split_bf16(y, hy, ly);
+  hi = pack_bf16(hx, hy);
+  lo = pack_bf16(lx, ly);
+}
+
+// four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(smem_row)));
+}
+
+// transposed variant: each 8x8 matrix is delivered transposed (B operand of a [k][n] row-major tile)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(ptx::smem_u32(smem_row)));
+}
+
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills the destination (src must still be a valid address)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+}  // namespace alm

@@ -47,6 +47,22 @@ Lin load_lin(Ctx* c, const std::map<std::string, HostTensor>& t, const std::stri
   return l;
 }
 
+// Swin qkv projection with the attention scale folded into the q rows (swin_transformer.py:130 multiplies q by
+// head_dim^-0.5 right after the projection): the GEMM epilogue then emits the operand planes of q*scale directly
+Lin load_qkv_qscaled(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int C) {
+  const HostTensor& w = need(t, p + ".weight");
+  const HostTensor& b = need(t, p + ".bias");
+  ALM_REQUIRE(static_cast<long>(w.numel()) == 3L * C * C && static_cast<long>(b.numel()) == 3L * C, ALM_ERR_INVALID,
+              "qkv shape mismatch at " + p);
+  std::vector<float> ws(w.f32), bs(b.f32);
+  for (size_t i = 0; i < static_cast<size_t>(C) * C; ++i) ws[i] *= WATTN_QSCALE;
+  for (int i = 0; i < C; ++i) bs[i] *= WATTN_QSCALE;
+  Lin l;
+  l.w = upload_split(c, ws.data(), 3 * C, C, 0);
+  l.b = upload_f32(c, bs.data(), bs.size());
+  return l;
+}
+
 // rows [r0, r0+n) of a packed in_proj weight/bias
 Lin load_inproj_rows(Ctx* c, const std::map<std::string, HostTensor>& t, const std::string& p, int r0, int n) {
   const HostTensor& w = need(t, p + ".in_proj_weight");
@@ -113,7 +129,7 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
       SwinBlockW& w = m->stage[s].blocks[b];
       w.n1 = load_ln(c, t, p + "norm1", C);
       w.n2 = load_ln(c, t, p + "norm2", C);
-      w.qkv = load_lin(c, t, p + "attn.qkv", 3 * C, C);
+      w.qkv = load_qkv_qscaled(c, t, p + "attn.qkv", C);
       w.proj = load_lin(c, t, p + "attn.proj", C, C);
       w.fc1 = load_lin(c, t, p + "mlp.fc1", 4 * C, C);
       w.fc2 = load_lin(c, t, p + "mlp.fc2", C, 4 * C);
@@ -266,7 +282,7 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     window_map(c, map0, B, Hc, Wc, nWh, nWw, 0);
     window_map(c, map1, B, Hc, Wc, nWh, nWw, 3);
     SplitBuf lnw = alloc_split(c, std::max(rowsP, rows) * C);
-    float* qkv = ws.get<float>(rowsP * 3 * C);
+    SplitBuf qkv = alloc_split(c, rowsP * 3 * C);
     SplitBuf att = alloc_split(c, rowsP * C);
     SplitBuf hid = alloc_split(c, rows * 4 * C);
     for (int b = 0; b < kDepths[s]; ++b) {
@@ -276,8 +292,9 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
       // LN1 -> zero-pad -> roll -> window partition, as one gather (pad tokens stay live keys, F10)
       gather_ln(c, x, C, map, 1, C, rowsP, w.n1.g, w.n1.b, 1e-5f, true, nullptr, 0, nullptr, 0, lnw.hi, lnw.lo, C,
                 nullptr, nullptr);
-      linear(c, lnw, rowsP, w.qkv, ACT_NONE, qkv, nullptr);
-      window_attention(c, qkv, C, heads, nWh, nWw, B, shift, nWh * 7, nWw * 7, w.bias_dense, att.hi, att.lo, nullptr);
+      linear(c, lnw, rowsP, w.qkv, ACT_NONE, nullptr, &qkv);
+      window_attention_split(c, qkv.hi, qkv.lo, C, heads, nWh, nWw, B, shift, nWh * 7, nWw * 7, w.bias_dense, att.hi,
+                             att.lo, nullptr);
       // proj + window reverse + un-roll + crop + residual, fused in the GEMM epilogue (scatter map)
       linear(c, att, rowsP, w.proj, ACT_NONE, x, nullptr, x, map, nullptr, C);
       gather_ln(c, x, C, nullptr, 1, C, rows, w.n2.g, w.n2.b, 1e-5f, false, nullptr, 0, nullptr, 0, lnw.hi, lnw.lo, C,
@@ -350,6 +367,10 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
     gemm(c, a, w, e);
   }
+  if (m->Mpad != m->M) {  // pad columns M..Mpad-1 of V_c^T must be finite zeros: the fused attention multiplies them by p = 0
+    ALM_CHECK_CUDA(cudaMemsetAsync(m->vt_hi, 0, static_cast<size_t>(B) * 6144 * m->Mpad * sizeof(bf16), c->stream));
+    ALM_CHECK_CUDA(cudaMemsetAsync(m->vt_lo, 0, static_cast<size_t>(B) * 6144 * m->Mpad * sizeof(bf16), c->stream));
+  }
   {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
     Operand bop = act_op(mem.hi, mem.lo, m->M, 512, 512);
     bop.nb1 = B; bop.bs1 = static_cast<long>(m->M) * 512;
@@ -380,6 +401,8 @@ struct DecodeBufs {
   float* xq_partial = nullptr;  // fused single-query cross-attention: split partials + counters
   int* xq_counters = nullptr;
   int xq_splits = 1;
+  int mq_splits = 1, mq_bps = 1;  // fused multi-query cross-attention: key splits, key blocks per split
+  bool fused_xattn = false;
   SplitBuf prob;
   float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
   float* vc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -410,7 +433,14 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     d.h1f = c->ws.get<float>(S * 512);
     d.qkv = c->ws.get<float>(S * 1536);
   }
-  if (Ncap == 1) {
+  if (c->xattn_impl == 0) {
+    int pairs = 0;
+    d.fused_xattn = true;
+    cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_splits, &d.mq_bps, &pairs);
+    d.xq_partial = c->ws.get<float>(cross_attn_mq_partial_floats(pairs, d.mq_splits));
+    d.xq_counters = c->ws.get<int>(pairs);
+    fill_i32(c, d.xq_counters, pairs, 0);
+  } else if (Ncap == 1) {
     d.xq_splits = cross_attn_q1_splits(c, B, m->M);
     d.xq_partial = c->ws.get<float>(static_cast<size_t>(B) * 8 * d.xq_splits * 66);
     d.xq_counters = c->ws.get<int>(static_cast<size_t>(B) * 8);
@@ -455,9 +485,14 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       lin(u.lnpf, 512, w.ca_q, ACT_NONE, u.qf, nullptr);
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
-      cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                    m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, nullptr,
-                    nullptr, u.of);
+      if (u.fused_xattn)
+        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial, u.xq_counters,
+                      nullptr, nullptr, u.of);
+      else
+        cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                      m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, nullptr,
+                      nullptr, u.of);
       lin(u.of, 512, w.ca_out, ACT_NONE, u.x, u.x);
       gather_ln(c, u.x, 512, nullptr, 1, 512, S, w.n3.g, w.n3.b, 1e-5f, false, nullptr, 0, u.lnf, 512, nullptr, nullptr, 512,
                 nullptr, nullptr);
@@ -490,9 +525,22 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, u.qf, nullptr);
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
-      cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                    m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, u.o.hi,
-                    u.o.lo);
+      if (u.fused_xattn)
+        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial, u.xq_counters,
+                      u.o.hi, u.o.lo, nullptr);
+      else
+        cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
+                      m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, u.o.hi,
+                      u.o.lo);
+    } else if (u.fused_xattn) {
+      // Ncap queries per image: scores, mask, online softmax and P.V fused; K_c / V_c^T streamed once per layer-step
+      linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
+      const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
+      const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
+      cross_attn_mq(c, u.q.hi, u.q.lo, nullptr, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff,
+                    m->vt_lo + voff, m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial,
+                    u.xq_counters, u.o.hi, u.o.lo, nullptr);
     } else {
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
       {
@@ -568,7 +616,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {

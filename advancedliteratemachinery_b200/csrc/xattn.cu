@@ -1,0 +1,402 @@
+// Fused multi-query cross-attention for the batched poly / rec decode loops (transformer.py:444-447 with
+// Ncap live sequences per image): per (image, head, 64-query block)
+//     S = (q / 8) K_c^T  ->  key-padding mask  ->  online softmax  ->  O = P V_c
+// in ONE pass over the cached split-bf16 K_c / V_c^T of the image, flash-attention style: the [S*8, M] score and
+// probability matrices never touch HBM (they were 4 x 134 MB per layer-step at 16 pages x 64 instances).
+// Both products run on mma.sync.m16n8k16 with the three-term split hi*hi + lo*hi + hi*lo accumulated in fp32 --
+// the same fp32-class scheme as the GEMM engine; softmax statistics stay in fp32 registers.  64-query tiles are
+// half a tcgen05 instruction's rows, so the warp-level MMA is the right granularity (see kernels.cu, window
+// attention).  HBM floor: K_c + V_c of one decoder layer are streamed once per layer-step.
+//
+//   grid (nimg * 8 * nqb, key_splits); 4 warps, warp w owns query rows 16w..16w+15 of the block.
+//   Q16 variant (<= 16 sequences per image: the pt loop has ONE): all four warps share the single 16-row query
+//   tile and split every 64-key block four ways (16 keys each), so the MMA work drops 4x and the kernel is purely
+//   HBM-bound on the K_c / V_c^T stream; each warp publishes its own (m, l, o) partial.
+//   Key blocks of 64 are staged with cp.async into a 2-stage ring (hi/lo planes of K [key][dim] and V^T [dim][key],
+//   144-byte pitch -> conflict-free ldmatrix).  Split partials (m, l, o[64]) are merged by the last CTA of each
+//   (image, head, query block) through a self-resetting counter, so one launch suffices.
+#include <algorithm>
+
+#include "mma.cuh"
+#include "omni.h"
+
+namespace alm {
+namespace {
+
+constexpr int MQ_KB = 64;                     // keys per block
+constexpr int MQ_PITCH = 72;                  // bf16 per staged row (64 + 8 pad)
+constexpr int MQ_PLANE = 64 * MQ_PITCH;       // one plane tile (64 rows)
+constexpr int MQ_STAGE = 4 * MQ_PLANE;        // K hi, K lo, V^T hi, V^T lo
+constexpr int MQ_STAGES = 2;
+constexpr int MQ_SMEM = MQ_STAGES * MQ_STAGE * 2 + MQ_STAGES * MQ_KB;  // tiles + per-stage key mask bytes
+constexpr int MQ_PART = 66;                   // floats per partial row: m, l, o[64]
+
+template <int NS, bool Q16>
+__global__ void __launch_bounds__(128, 3)
+cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, const float* __restrict__ q_f32, int Ncap,
+                     const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo, const bf16* __restrict__ vt_hi,
+                     const bf16* __restrict__ vt_lo, const uint8_t* __restrict__ kpm, int M, int Mpad, int nqb,
+                     int blocks_per_split, float* __restrict__ partial, int* __restrict__ counters,
+                     bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
+  constexpr int NJ = Q16 ? 2 : 8;    // 8-key n-tiles of a block this warp scores
+  constexpr int NKK = Q16 ? 1 : 4;   // 16-key k-steps of a block this warp feeds into P.V
+  extern __shared__ __align__(16) unsigned char mq_smem[];
+  bf16* tiles = reinterpret_cast<bf16*>(mq_smem);
+  uint8_t* smask = mq_smem + MQ_STAGES * MQ_STAGE * 2;
+  __shared__ int last_flag;
+
+  const int pair = blockIdx.x, qb = pair % nqb, ih = pair / nqb, h = ih & 7, img = ih >> 3;
+  const int split = blockIdx.y, gs = gridDim.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nkb = (M + MQ_KB - 1) / MQ_KB;
+  const int kb0 = split * blocks_per_split, kb1 = min(nkb, kb0 + blocks_per_split);
+  const int q0 = qb * 64;
+  const int j0 = Q16 ? 2 * warp : 0, kk0 = Q16 ? warp : 0;
+  const int r_lo = (Q16 ? 0 : warp * 16) + g, r_hi = r_lo + 8;  // the two query rows (within the block) this lane holds
+  const bool live_lo = q0 + r_lo < Ncap, live_hi = q0 + r_hi < Ncap;
+
+  // ---- A fragments of q (hi, lo) for the four 16-dim k-steps, straight from global memory (read once)
+  constexpr int NP = (NS == 3) ? 2 : 1;
+  uint32_t aq[NP][4][4];
+  {
+    const long row_lo = (static_cast<long>(img) * Ncap + q0 + r_lo) * 512 + h * 64;
+    const long row_hi = (static_cast<long>(img) * Ncap + q0 + r_hi) * 512 + h * 64;
+    if (q_f32) {  // fp32 queries (pt loop): split on the fly
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int c0 = ks * 16 + 2 * t;
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 v0 = live_lo ? *reinterpret_cast<const float2*>(q_f32 + row_lo + c0) : z;
+        const float2 v1 = live_hi ? *reinterpret_cast<const float2*>(q_f32 + row_hi + c0) : z;
+        const float2 v2 = live_lo ? *reinterpret_cast<const float2*>(q_f32 + row_lo + c0 + 8) : z;
+        const float2 v3 = live_hi ? *reinterpret_cast<const float2*>(q_f32 + row_hi + c0 + 8) : z;
+        uint32_t l0, l1, l2, l3;
+        split_pack2(v0.x, v0.y, aq[0][ks][0], l0);
+        split_pack2(v1.x, v1.y, aq[0][ks][1], l1);
+        split_pack2(v2.x, v2.y, aq[0][ks][2], l2);
+        split_pack2(v3.x, v3.y, aq[0][ks][3], l3);
+        if (NS == 3) { aq[NP - 1][ks][0] = l0; aq[NP - 1][ks][1] = l1; aq[NP - 1][ks][2] = l2; aq[NP - 1][ks][3] = l3; }
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const bf16* qp = p == 0 ? q_hi : q_lo;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const int c0 = ks * 16 + 2 * t;
+          aq[p][ks][0] = live_lo ? *reinterpret_cast<const uint32_t*>(qp + row_lo + c0) : 0u;
+          aq[p][ks][1] = live_hi ? *reinterpret_cast<const uint32_t*>(qp + row_hi + c0) : 0u;
+          aq[p][ks][2] = live_lo ? *reinterpret_cast<const uint32_t*>(qp + row_lo + c0 + 8) : 0u;
+          aq[p][ks][3] = live_hi ? *reinterpret_cast<const uint32_t*>(qp + row_hi + c0 + 8) : 0u;
+        }
+      }
+    }
+  }
+
+  const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;           // K_c[img][dl(base)][h][key][64]
+  const long vbase = (static_cast<long>(img) * 6144 + h * 64) * Mpad;      // V_c^T[img][dl(base)*512 + h*64 + dim][key]
+  auto load_block = [&](int kb, int stage) {
+    bf16* st = tiles + stage * MQ_STAGE;
+    const int key0 = kb * MQ_KB;
+#pragma unroll
+    for (int i = tid; i < 512; i += 128) {
+      const int r = i >> 3, ch = (i & 7) * 8;
+      {  // K row r = key, 8 dims per 16-byte chunk; keys >= M are zero-filled
+        const int key = key0 + r;
+        const bool ok = key < M;
+        const long src = kbase + static_cast<long>(ok ? key : 0) * 64 + ch;
+        cp_async16(st + r * MQ_PITCH + ch, kc_hi + src, ok ? 16 : 0);
+        if (NS == 3) cp_async16(st + MQ_PLANE + r * MQ_PITCH + ch, kc_lo + src, ok ? 16 : 0);
+      }
+      {  // V^T row r = dim, 8 keys per chunk; chunks at or beyond Mpad are zero-filled (Mpad % 8 == 0; the pad
+         // columns M..Mpad-1 are kept zero by the encoder)
+        const int key = key0 + ch;
+        const bool ok = key < Mpad;
+        const long src = vbase + static_cast<long>(r) * Mpad + (ok ? key : 0);
+        cp_async16(st + 2 * MQ_PLANE + r * MQ_PITCH + ch, vt_hi + src, ok ? 16 : 0);
+        if (NS == 3) cp_async16(st + 3 * MQ_PLANE + r * MQ_PITCH + ch, vt_lo + src, ok ? 16 : 0);
+      }
+    }
+    if (tid < MQ_KB) {
+      const int key = key0 + tid;
+      smask[stage * MQ_KB + tid] = (key < M) ? (kpm ? kpm[static_cast<long>(img) * M + key] : 0) : 1;
+    }
+  };
+
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  const int lrow = lane & 7, lcol = (lane >> 3) * 8;  // ldmatrix.x4: row within the 8-row group, 8-column chunk
+
+  if (kb0 < kb1) {
+    load_block(kb0, 0);
+    cp_async_commit();
+  }
+  for (int kb = kb0; kb < kb1; ++kb) {
+    const int stage = (kb - kb0) & 1;
+    if (kb + 1 < kb1) {
+      load_block(kb + 1, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bf16* sKh = tiles + stage * MQ_STAGE;
+    const bf16* sKl = sKh + MQ_PLANE;
+    const bf16* sVh = sKh + 2 * MQ_PLANE;
+    const bf16* sVl = sKh + 3 * MQ_PLANE;
+    // ---- S = q K^T over this warp's keys of the block (n-tiles of 8 keys, 4 k-steps of 16 dims)
+    float s[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      uint32_t bh[2][4], bl[2][4];
+      const int roff = (8 * (j0 + j) + lrow) * MQ_PITCH + lcol;
+      ldmatrix_x4(bh[0], sKh + roff);
+      ldmatrix_x4(bh[1], sKh + roff + 32);
+      if (NS == 3) {
+        ldmatrix_x4(bl[0], sKl + roff);
+        ldmatrix_x4(bl[1], sKl + roff + 32);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = bh[ks >> 1][(ks & 1) * 2], b1 = bh[ks >> 1][(ks & 1) * 2 + 1];
+        mma_bf16_16816(s[j], aq[0][ks], b0, b1);
+        if (NS == 3) {
+          mma_bf16_16816(s[j], aq[NP - 1][ks], b0, b1);
+          mma_bf16_16816(s[j], aq[0][ks], bl[ks >> 1][(ks & 1) * 2], bl[ks >> 1][(ks & 1) * 2 + 1]);
+        }
+      }
+    }
+    // ---- scale (q / 8 == scores / 8 exactly), key-padding mask, online softmax update
+    const uint8_t* mk = smask + stage * MQ_KB;
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const uint32_t mm = *reinterpret_cast<const uint16_t*>(mk + 8 * (j0 + j) + 2 * t);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool dead = (mm >> (8 * e)) & 0xffu;
+        s[j][e] = dead ? -INFINITY : s[j][e] * 0.125f;
+        s[j][2 + e] = dead ? -INFINITY : s[j][2 + e] * 0.125f;
+        mx_lo = fmaxf(mx_lo, s[j][e]);
+        mx_hi = fmaxf(mx_hi, s[j][2 + e]);
+      }
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+    const float mu_lo = (mn_lo == -INFINITY) ? 0.f : mn_lo, mu_hi = (mn_hi == -INFINITY) ? 0.f : mn_hi;
+    const float sc_lo = expf(m_lo - mu_lo), sc_hi = expf(m_hi - mu_hi);  // exp(-inf) == 0 on the first live block
+    m_lo = mn_lo; m_hi = mn_hi;
+    l_lo *= sc_lo; l_hi *= sc_hi;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= sc_lo; o[n][1] *= sc_lo;
+      o[n][2] *= sc_hi; o[n][3] *= sc_hi;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[j][e] = expf(s[j][e] - mu_lo);
+        s[j][2 + e] = expf(s[j][2 + e] - mu_hi);
+        l_lo += s[j][e];
+        l_hi += s[j][2 + e];
+      }
+    // ---- O += P V : P (unnormalised, split) is the A operand straight from the accumulator fragments
+    uint32_t ph[NKK][4], pl[NKK][4];
+#pragma unroll
+    for (int kk = 0; kk < NKK; ++kk) {
+      split_pack2(s[2 * kk][0], s[2 * kk][1], ph[kk][0], pl[kk][0]);
+      split_pack2(s[2 * kk][2], s[2 * kk][3], ph[kk][1], pl[kk][1]);
+      split_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[kk][2], pl[kk][2]);
+      split_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[kk][3], pl[kk][3]);
+    }
+    if (Q16) {
+      // this warp's 16 keys only: one ldmatrix.x4 covers (b0, b1) of two consecutive dim tiles
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vh[4], vl[4];
+        const int roff = (8 * (2 * np + (lane >> 4)) + lrow) * MQ_PITCH + 16 * kk0 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(vh, sVh + roff);
+        if (NS == 3) ldmatrix_x4(vl, sVl + roff);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          mma_bf16_16816(o[2 * np + q], ph[0], vh[2 * q], vh[2 * q + 1]);
+          if (NS == 3) {
+            mma_bf16_16816(o[2 * np + q], pl[0], vh[2 * q], vh[2 * q + 1]);
+            mma_bf16_16816(o[2 * np + q], ph[0], vl[2 * q], vl[2 * q + 1]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        uint32_t vh[2][4], vl[2][4];
+        const int roff = (8 * n + lrow) * MQ_PITCH + lcol;
+        ldmatrix_x4(vh[0], sVh + roff);
+        ldmatrix_x4(vh[1], sVh + roff + 32);
+        if (NS == 3) {
+          ldmatrix_x4(vl[0], sVl + roff);
+          ldmatrix_x4(vl[1], sVl + roff + 32);
+        }
+#pragma unroll
+        for (int kk = 0; kk < NKK; ++kk) {
+          const uint32_t b0 = vh[kk >> 1][(kk & 1) * 2], b1 = vh[kk >> 1][(kk & 1) * 2 + 1];
+          mma_bf16_16816(o[n], ph[kk], b0, b1);
+          if (NS == 3) {
+            mma_bf16_16816(o[n], pl[kk], b0, b1);
+            mma_bf16_16816(o[n], ph[kk], vl[kk >> 1][(kk & 1) * 2], vl[kk >> 1][(kk & 1) * 2 + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with this stage before the next iteration's cp.async overwrites it
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+
+  if (!Q16 && gs == 1) {
+    const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+    const long ob_lo = (static_cast<long>(img) * Ncap + q0 + r_lo) * 512 + h * 64 + 2 * t;
+    const long ob_hi = (static_cast<long>(img) * Ncap + q0 + r_hi) * 512 + h * 64 + 2 * t;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      uint32_t hh, ll;
+      if (live_lo) {
+        split_pack2(o[n][0] * inv_lo, o[n][1] * inv_lo, hh, ll);
+        *reinterpret_cast<uint32_t*>(out_hi + ob_lo + 8 * n) = hh;
+        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + ob_lo + 8 * n) = ll;
+      }
+      if (live_hi) {
+        split_pack2(o[n][2] * inv_hi, o[n][3] * inv_hi, hh, ll);
+        *reinterpret_cast<uint32_t*>(out_hi + ob_hi + 8 * n) = hh;
+        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + ob_hi + 8 * n) = ll;
+      }
+    }
+    return;
+  }
+  // ---- publish (m, l, o[64]) per query row and partial; the last CTA of the pair merges.  A partial is one key
+  //      split (64 rows) or, for Q16, one warp of one key split (16 rows).
+  constexpr int PR = Q16 ? 16 : 64;           // rows per partial
+  const int nparts = Q16 ? gs * 4 : gs;
+  {
+    const int part = Q16 ? split * 4 + warp : split;
+    float* p_lo = partial + ((static_cast<long>(pair) * nparts + part) * PR + r_lo) * MQ_PART;
+    float* p_hi = partial + ((static_cast<long>(pair) * nparts + part) * PR + r_hi) * MQ_PART;
+    if (t == 0) {
+      p_lo[0] = m_lo; p_lo[1] = l_lo;
+      p_hi[0] = m_hi; p_hi[1] = l_hi;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      *reinterpret_cast<float2*>(p_lo + 2 + 8 * n + 2 * t) = make_float2(o[n][0], o[n][1]);
+      *reinterpret_cast<float2*>(p_hi + 2 + 8 * n + 2 * t) = make_float2(o[n][2], o[n][3]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_flag = (atomicAdd(&counters[pair], 1) == gs - 1);
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  {
+    constexpr int DPT = Q16 ? 8 : 32;         // dims per merging thread
+    const int row = Q16 ? tid >> 3 : tid >> 1, half = Q16 ? (tid & 7) * 8 : (tid & 1) * 32;
+    if (q0 + row < Ncap) {
+      const float* base = partial + (static_cast<long>(pair) * nparts * PR + row) * MQ_PART;
+      const long sstride = static_cast<long>(PR) * MQ_PART;
+      float mm = -INFINITY;
+      for (int sidx = 0; sidx < nparts; ++sidx) mm = fmaxf(mm, base[sidx * sstride]);
+      float ltot = 0.f, acc[DPT];
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+      for (int sidx = 0; sidx < nparts; ++sidx) {
+        const float* ps = base + sidx * sstride;
+        const float ms = ps[0];
+        const float w = (ms == -INFINITY) ? 0.f : expf(ms - mm);
+        ltot += w * ps[1];
+#pragma unroll
+        for (int i = 0; i < DPT; i += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(ps + 2 + half + i);
+          acc[i] = fmaf(w, v.x, acc[i]);
+          acc[i + 1] = fmaf(w, v.y, acc[i + 1]);
+        }
+      }
+      const float inv = 1.0f / ltot;
+      const long ob = (static_cast<long>(img) * Ncap + q0 + row) * 512 + h * 64 + half;
+#pragma unroll
+      for (int i = 0; i < DPT; i += 8) {
+        if (out_f32) {
+          *reinterpret_cast<float4*>(out_f32 + ob + i) = make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv);
+          *reinterpret_cast<float4*>(out_f32 + ob + i + 4) = make_float4(acc[i + 4] * inv, acc[i + 5] * inv, acc[i + 6] * inv, acc[i + 7] * inv);
+        }
+        if (out_hi) {
+          uint4 hh, ll;
+          split_pack2(acc[i] * inv, acc[i + 1] * inv, hh.x, ll.x);
+          split_pack2(acc[i + 2] * inv, acc[i + 3] * inv, hh.y, ll.y);
+          split_pack2(acc[i + 4] * inv, acc[i + 5] * inv, hh.z, ll.z);
+          split_pack2(acc[i + 6] * inv, acc[i + 7] * inv, hh.w, ll.w);
+          *reinterpret_cast<uint4*>(out_hi + ob + i) = hh;
+          if (out_lo) *reinterpret_cast<uint4*>(out_lo + ob + i) = ll;
+        }
+      }
+    }
+  }
+  if (tid == 0) counters[pair] = 0;  // ready for the next launch (graph replay)
+}
+
+}  // namespace
+
+// Split plan: ~3 resident CTAs per SM (the kernel's occupancy), at least two key blocks per CTA.
+void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* key_splits, int* blocks_per_split, int* pairs) {
+  const int nqb = (Ncap + 63) / 64;
+  const int np = nimg * 8 * nqb;
+  const int nkb = (M + MQ_KB - 1) / MQ_KB;
+  int gs = std::max(1, (3 * c->num_sms) / np);
+  gs = std::min(gs, std::max(1, nkb / 2));
+  const int bps = (nkb + gs - 1) / gs;
+  *key_splits = (nkb + bps - 1) / bps;
+  *blocks_per_split = bps;
+  *pairs = np;
+}
+
+size_t cross_attn_mq_partial_floats(int pairs, int key_splits) {
+  return static_cast<size_t>(pairs) * key_splits * 64 * MQ_PART;  // Q16: 4 warps x 16 rows per split -- same size
+}
+
+void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
+                   const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo, const uint8_t* kpm, int M, int Mpad,
+                   int key_splits, int blocks_per_split, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
+                   float* out_f32) {
+  const int nqb = (Ncap + 63) / 64;
+  static bool attr = false;
+  if (!attr) {
+    auto prep = [](auto* k) {
+      ALM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, MQ_SMEM));
+      pin_carveout(k);
+    };
+    prep(cross_attn_mq_kernel<3, false>); prep(cross_attn_mq_kernel<1, false>);
+    prep(cross_attn_mq_kernel<3, true>); prep(cross_attn_mq_kernel<1, true>);
+    attr = true;
+  }
+  ALM_REQUIRE((Mpad & 7) == 0, ALM_ERR_INVALID, "cross_attn_mq: Mpad must be a multiple of 8");
+  ALM_REQUIRE(q_f32 || q_hi, ALM_ERR_INVALID, "cross_attn_mq: no query operand");
+  const bool q16 = Ncap <= 16;
+  ALM_REQUIRE(q16 || (out_hi && !out_f32), ALM_ERR_INVALID, "cross_attn_mq: fp32 output only on the <= 16-query path");
+  const bool three = c->nsplit == 3 && (q_f32 || q_lo) && kc_lo && vt_lo;
+  dim3 grid(nimg * 8 * nqb, key_splits);
+#define ALM_MQ_LAUNCH(NS, Q)                                                                                            \
+  cross_attn_mq_kernel<NS, Q><<<grid, 128, MQ_SMEM, c->stream>>>(q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vt_hi, vt_lo, kpm, \
+                                                                 M, Mpad, nqb, blocks_per_split, partial, counters,     \
+                                                                 out_hi, out_lo, out_f32)
+  if (three) { if (q16) ALM_MQ_LAUNCH(3, true); else ALM_MQ_LAUNCH(3, false); }
+  else       { if (q16) ALM_MQ_LAUNCH(1, true); else ALM_MQ_LAUNCH(1, false); }
+#undef ALM_MQ_LAUNCH
+  count_launch(c); check_launch("cross_attn_mq");
+}
+
+}  // namespace alm

@@ -184,6 +184,7 @@ def main():
     ap.add_argument('--grid-cap', type=int, default=0)
     ap.add_argument('--inflight', type=int, default=3, help='independent batches in flight per GPU (one context + stream '
                     'each); the per-token decode loops are latency-bound, so concurrent batches fill the idle SMs')
+    ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
     ap.add_argument('--cpu-sample', nargs=2, type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_sample:
@@ -221,6 +222,8 @@ def main():
         cx.set_option('workspace_mb', 20480)
         if args.grid_cap:
             cx.set_option('small_grid_cap', args.grid_cap)
+        for kv in args.opt:
+            cx.set_option(kv.split('=')[0], int(kv.split('=')[1]))
         ctxs.append(cx)
         models.append(OmniParserB200(sd, vocab, ctx=cx))
     del sd
@@ -342,7 +345,7 @@ def main():
         'data': 'synthetic',
         'config': {'workload': f'OmniParser Swin-B text spotting, {PAGE}x{PAGE} synthetic pages, batch {B} per GPU, '
                                f'N={N_INST} instances/page pinned (pt 128 + poly 32 + rec {REC_LEN} tokens)',
-                   'global_batch': world * B, 'parallelism': f'dp{world}', 'in_flight_batches_per_gpu': C_, 'l2': 'inputs (201 MB/step) and activations '
+                   'global_batch': world * B, 'parallelism': f'dp{world}', 'in_flight_batches_per_gpu': C_, **({'options': args.opt} if args.opt else {}), 'l2': 'inputs (201 MB/step) and activations '
                    'exceed the 126 MB L2; no explicit flush', 'weights': 'synthetic seed 0 (advancedliteratemachinery_b200/synthetic.py), pt_eos pinned'},
         'decoded_chars_per_sec': world * n_chars / (ms_per_step * 1e-3),
         'encoder_ms_per_batch': enc_ms,

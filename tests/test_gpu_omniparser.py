@@ -349,3 +349,42 @@ def test_full_size_page_encoder_matches_oracle():
     assert m.encode(img.cuda(), None) == (1, 64, 64) and hw == (64, 64)
     assert _rel(m.memory(0), mem) < 1e-4
     assert float((m.memory(1) - pos).abs().max()) < 5e-6
+
+
+def test_fused_cross_attention_matches_gemm_path_and_oracle():
+    """The flash-style fused cross-attention (xattn.cu) against the unfused paths (score GEMM + softmax + P.V GEMM;
+    fp32 single-query kernel) and the oracle: 70 sequences of one image (two 64-query blocks, 58 dead rows), 10 and 1
+    sequences (the 16-row variant the pt loop uses), M = 15 x 17 = 255 keys (ragged last key block, Mpad = 256, two key
+    splits), right-hand columns masked."""
+    from oracle import omniparser_ref as O
+    from tests.conftest import omni_sd
+    sd = omni_sd(0, 0.45)
+    m = model_for(0, 0.45)
+    v = m.vocab
+    g = torch.Generator().manual_seed(77)
+    img = torch.randn(1, 3, 240, 272, generator=g)
+    mask = torch.zeros(1, 240, 272, dtype=torch.bool)
+    mask[:, :, 224:] = True
+    img[mask[:, None].expand_as(img)] = 0
+    n_seq, L = 70, 5
+    seq = torch.cat([torch.randint(0, v.num_bins, (n_seq, 2), generator=g), torch.full((n_seq, 1), v.rec_sos_index),
+                     torch.randint(v.num_bins, v.recog_pad_index, (n_seq, L - 3), generator=g)], 1)
+    m.encode(img, mask)
+    _, mh, mw = m.memory_shape()
+    assert mh * mw == 255
+    mem_o, pos_o, kpm_o, _ = O.encode(img, mask, sd)
+    assert bool(kpm_o[0].any()) and not bool(kpm_o[0].all())
+    ref = O.decode_logits(seq[:8], mem_o[0], kpm_o[0], pos_o[0], sd, 'rec')
+    for n in (70, 10, 1):
+        lg = {}
+        try:
+            for impl in (0, 1):
+                m.ctx.set_option('xattn_impl', impl)
+                lg[impl] = m.decode_logits(0, 'rec', seq[:n])
+        finally:
+            m.ctx.set_option('xattn_impl', 0)
+        assert torch.isfinite(lg[0]).all()
+        assert _maxrel(lg[0], lg[1]) < 2e-5, (n, _maxrel(lg[0], lg[1]))
+        k = min(n, 8)
+        assert _maxrel(lg[0][:k], ref[:k]) < LOGIT_REL_TOL
+        assert _rel(lg[0][:k], ref[:k]) < 1e-4
