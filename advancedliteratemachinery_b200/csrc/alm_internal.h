@@ -156,6 +156,20 @@ struct Ctx {
     }
   };
   std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
+  // Co-scheduling of in-flight batches: every tcgen05 GEMM CTA needs a whole SM (231 KB of shared memory) for the
+  // whole launch, so a full-width encoder GEMM shuts every other stream out.  enc_grid_cap / dec_grid_cap bound the
+  // persistent GEMM grids of the encoder / the decode loops; decode_priority runs the decode loops on internal
+  // high-priority streams so that their short kernels are dispatched ahead of the encoder's wide elementwise grids.
+  int enc_grid_cap = 0, dec_grid_cap = 0;
+  int gemm_grid_cap = 0;  // cap in force (set by omni_encode / omni_decode)
+  int decode_priority = 0;
+  // timing experiments only (tools/concurrency_probe.py): inside the decoder layers drop the launches of a kernel
+  // class (bit 0 cross-attention, 1 linears, 2 LayerNorm, 3 self-attention).  Results are garbage by construction.
+  int debug_skip = 0;
+  bool skip_scope = false;
+  bool skipped(int bit) const { return skip_scope && (debug_skip & bit); }
+  cudaStream_t stream_hi = nullptr;  // internal high-priority stream for the decode loops
+  cudaEvent_t ev_prio = nullptr;
   int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
   int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial
@@ -164,6 +178,8 @@ struct Ctx {
   int* trace_idx = nullptr;
   int trace_cap = 0;
   unsigned long long* detail_buf = nullptr;  // [64][6] per-role stamps of CTA 0, overwritten by every GEMM (debug)
+  int sattn_wide = 1;  // CTA-per-(sequence, head) self-attention step when there are few sequences
+  int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
   int xattn_impl = 0;  // 0 = fused flash-style multi-query cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)

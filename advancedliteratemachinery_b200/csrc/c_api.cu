@@ -145,6 +145,8 @@ void alm_free(alm_ctx* h) {
   if (h->dev_in) cudaFree(h->dev_in);
   if (h->dev_mask) cudaFree(h->dev_mask);
   if (h->c.stream2) cudaStreamDestroy(h->c.stream2);
+  if (h->c.stream_hi) cudaStreamDestroy(h->c.stream_hi);
+  if (h->c.ev_prio) cudaEventDestroy(h->c.ev_prio);
   if (h->c.ev_fork) { cudaEventDestroy(h->c.ev_fork); cudaEventDestroy(h->c.ev_join); }
   for (auto e : h->c.ev_t) if (e) cudaEventDestroy(e);
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
@@ -180,6 +182,19 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
       h->c.xattn_impl = value ? 1 : 0;
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
+    } else if (k == "enc_grid_cap") {
+      h->c.enc_grid_cap = static_cast<int>(value);
+    } else if (k == "dec_grid_cap") {
+      h->c.dec_grid_cap = static_cast<int>(value);
+    } else if (k == "xattn_ctas_per_sm") {
+      ALM_REQUIRE(value >= 1 && value <= 3, ALM_ERR_INVALID, "xattn_ctas_per_sm must be 1..3");
+      h->c.xattn_ctas_per_sm = static_cast<int>(value);
+    } else if (k == "sattn_wide") {
+      h->c.sattn_wide = value ? 1 : 0;
+    } else if (k == "debug_skip") {
+      h->c.debug_skip = static_cast<int>(value);
+    } else if (k == "decode_priority") {
+      h->c.decode_priority = value ? 1 : 0;
     } else if (k == "small_grid_cap") {
       h->c.small_grid_cap = static_cast<int>(value);
     } else if (k == "wide_tiles") {

@@ -518,6 +518,7 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   // Small launches (the per-token decode GEMMs) leave half of the SMs to the kernels of the other in-flight
   // streams / batches: every CTA of this kernel needs a whole SM (231 KB of shared memory).
   long cap = c->num_sms;
+  if (c->gemm_grid_cap > 0) cap = std::min<long>(cap, c->gemm_grid_cap);
   if (c->small_grid_cap > 0 && p.num_tiles <= 2L * c->num_sms) cap = c->small_grid_cap;
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, cap));
   kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
@@ -526,6 +527,7 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
 }  // namespace
 
 void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
+  if (c->skipped(2)) return;
   ALM_REQUIRE(A.K == B.K, ALM_ERR_INVALID, "gemm: K mismatch");
   ALM_REQUIRE(A.rows > 0 && B.rows > 0 && A.K > 0, ALM_ERR_INVALID, "gemm: empty problem");
   ALM_REQUIRE(E.out_f32 || E.out_hi, ALM_ERR_INVALID, "gemm: no output");

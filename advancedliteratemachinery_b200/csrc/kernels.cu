@@ -460,13 +460,30 @@ template <int MR, int NW>  // MR = row capacity (8/16/32), NW = K / 128 float4 s
 __global__ void __launch_bounds__(128)
 gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int n_split, long ldx,
                  const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ resid, long ldr,
-                 float* __restrict__ out, long ldo, int M, int N, int K, int act, int use_smem) {
-  extern __shared__ __align__(16) float sx[];  // [M][K] activation rows (when they fit)
+                 float* __restrict__ out, long ldo, int M, int N, int K, int act) {
+  // activation rows, staged in K-chunks of <= 512 floats (double-buffered when K > 512): at most 64 KB for 16 rows,
+  // so this kernel co-resides with the HBM-bound attention CTAs of the other in-flight decode streams
+  extern __shared__ __align__(16) float sx[];
+  constexpr int NC = (NW + 3) / 4;          // chunks
+  constexpr int NWC = NW < 4 ? NW : 4;      // float4 slices per lane and chunk
+  const int KC = NC == 1 ? K : 512;         // chunk width (floats)
   const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const float* xin = (blockIdx.x * 4 < n_split) ? x : x2;  // columns [0, n_split) read x, the rest x2 (fused q|k|v)
-  // the whole weight row of this column is requested up front (NW independent 16-byte loads per lane = one HBM
-  // round trip) ...
+  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sx));
+  auto stage = [&](int chunk, int buf) {
+    const int k4 = KC >> 2;
+    for (int i = threadIdx.x; i < M * k4; i += 128) {
+      const int m = i / k4, c4 = i - m * k4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + static_cast<uint32_t>(((buf * M + m) * KC + c4 * 4) * 4)),
+                   "l"(xin + m * ldx + chunk * KC + c4 * 4)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);  // every 16-byte copy of the chunk is in flight at once: one memory round trip however many rows
+  // the whole weight row of this column is requested up front (NW independent 16-byte loads per lane = one
+  // round trip), overlapping the activation staging
   float4 w[NW];
   if (n < N) {
     const float* wrow = W + static_cast<long>(n) * K;
@@ -475,42 +492,46 @@ gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int 
       const int k0 = (i * 32 + lane) * 4;
       w[i] = k0 < K ? *reinterpret_cast<const float4*>(wrow + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // ... while the CTA stages the few activation rows in shared memory with cp.async: every 16-byte copy is in
-  // flight at once, so the staging costs one memory round trip however many rows there are
-  if (use_smem) {
-    const int k4 = K >> 2;
-    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sx));
-    for (int i = threadIdx.x; i < M * k4; i += 128) {
-      const int m = i / k4, c4 = i - m * k4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + static_cast<uint32_t>((m * K + c4 * 4) * 4)),
-                   "l"(xin + m * ldx + c4 * 4)
-                   : "memory");
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) {
+      stage(c + 1, (c + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-  }
-  if (n >= N) return;
-  const float* xs = use_smem ? sx : xin;
-  const long lds = use_smem ? K : ldx;
-  float mine = 0.f;
+    const float* xs = sx + static_cast<long>(c & 1) * M * KC;
 #pragma unroll
-  for (int m = 0; m < MR; ++m) {
-    float acc = 0.f;
-    if (m < M) {
+    for (int m = 0; m < MR; ++m) {
+      if (m < M) {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const int k0 = (i * 32 + lane) * 4;
-        if (k0 < K) {
-          const float4 a = *reinterpret_cast<const float4*>(xs + m * lds + k0);
-          acc = fmaf(a.x, w[i].x, acc); acc = fmaf(a.y, w[i].y, acc);
-          acc = fmaf(a.z, w[i].z, acc); acc = fmaf(a.w, w[i].w, acc);
+        for (int i = 0; i < NWC; ++i) {
+          const int kk = (i * 32 + lane) * 4;
+          if (c * KC + kk < K) {
+            const float4 a = *reinterpret_cast<const float4*>(xs + m * KC + kk);
+            const float4 ww = w[c * 4 + i];
+            acc[m] = fmaf(a.x, ww.x, acc[m]); acc[m] = fmaf(a.y, ww.y, acc[m]);
+            acc[m] = fmaf(a.z, ww.z, acc[m]); acc[m] = fmaf(a.w, ww.w, acc[m]);
+          }
         }
       }
     }
-    acc = warp_sum(acc);
-    if (lane == m) mine = acc;
+    if (c + 2 < NC) __syncthreads();  // the buffer is refilled two chunks later
+  }
+  if (n >= N) return;
+  float mine = 0.f;
+#pragma unroll
+  for (int m = 0; m < MR; ++m) {
+    const float v = warp_sum(acc[m]);
+    if (lane == m) mine = v;
   }
   if (lane < M && lane < MR) {
     float v = mine + (bias ? bias[n] : 0.f);
@@ -526,6 +547,7 @@ gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int 
 void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int Cs, long rows, const float* gamma,
                const float* beta, float eps, bool zero_missing, const float* add, long ld_add, float* out_f32,
                long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo, float* out2_f32) {
+  if (c->skipped(4)) return;
   if (rows == 0) return;
   const int C = nsrc * Cs;
   ALM_REQUIRE(C % 128 == 0 && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID, "gather_ln: width must be a multiple of 128");
@@ -615,23 +637,23 @@ void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint
 namespace alm {
 void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, const float* W, const float* bias,
                const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act) {
-  ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048 && n_split % 4 == 0, ALM_ERR_INVALID,
-              "gemv_rows: M <= 32, K % 4 == 0, K <= 2048");
+  if (c->skipped(2)) return;
+  ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048 && n_split % 4 == 0 &&
+                  (K <= 512 || K % 512 == 0),
+              ALM_ERR_INVALID, "gemv_rows: M <= 32, K % 4 == 0, K <= 512 or a multiple of 512 up to 2048");
   const unsigned grid = static_cast<unsigned>((N + 3) / 4);
-  const size_t sm = static_cast<size_t>(M) * K * sizeof(float);
-  const int use_smem = sm <= 160 * 1024;
-  const size_t dyn = use_smem ? sm : 0;
+  const size_t dyn = static_cast<size_t>(M) * (K <= 512 ? K : 2 * 512) * sizeof(float);
 #define ALM_GEMV(MRV, NWV)                                                                                         \
   do {                                                                                                             \
     static bool attr = false;                                                                                      \
     if (!attr) {                                                                                                   \
       ALM_CHECK_CUDA(cudaFuncSetAttribute(gemv_rows_kernel<MRV, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          160 * 1024));                                                            \
+                                          128 * 1024));                                                            \
       alm::pin_carveout(gemv_rows_kernel<MRV, NWV>);                                                               \
       attr = true;                                                                                                 \
     }                                                                                                              \
     gemv_rows_kernel<MRV, NWV><<<grid, 128, dyn, c->stream>>>(x, x2 ? x2 : x, n_split, ldx, W, bias, resid, ldr,   \
-                                                              out, ldo, M, N, K, act, use_smem);                  \
+                                                              out, ldo, M, N, K, act);                            \
   } while (0)
   const int nw = K <= 512 ? 4 : 16;
   if (M <= 8) { if (nw == 4) ALM_GEMV(8, 4); else ALM_GEMV(8, 16); }

@@ -230,6 +230,11 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   Arena& ws = c->ws;
   ws.off = 0;
   m->encoded = false;
+  struct CapGuard {
+    Ctx* c;
+    ~CapGuard() { c->gemm_grid_cap = 0; }
+  } cap_guard{c};
+  c->gemm_grid_cap = c->enc_grid_cap;
   if (!c->ev_t[0]) for (auto& e : c->ev_t) ALM_CHECK_CUDA(cudaEventCreate(&e));
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[0], c->stream));
   m->B = B; m->H = H; m->W = W;
@@ -401,7 +406,7 @@ struct DecodeBufs {
   float* xq_partial = nullptr;  // fused single-query cross-attention: split partials + counters
   int* xq_counters = nullptr;
   int xq_splits = 1;
-  int mq_splits = 1, mq_bps = 1;  // fused multi-query cross-attention: key splits, key blocks per split
+  int mq_grid = 1, mq_parts = 1;  // fused cross-attention: persistent grid size, partial slots per (image, head, query block)
   bool fused_xattn = false;
   SplitBuf prob;
   float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -436,8 +441,8 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
   if (c->xattn_impl == 0) {
     int pairs = 0;
     d.fused_xattn = true;
-    cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_splits, &d.mq_bps, &pairs);
-    d.xq_partial = c->ws.get<float>(cross_attn_mq_partial_floats(pairs, d.mq_splits));
+    cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
+    d.xq_partial = c->ws.get<float>(cross_attn_mq_partial_floats(pairs, d.mq_parts));
     d.xq_counters = c->ws.get<int>(pairs);
     fill_i32(c, d.xq_counters, pairs, 0);
   } else if (Ncap == 1) {
@@ -471,6 +476,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     auto lin = [&](const float* x, int K, const Lin& w, int act, float* out, const float* resid) {
       gemv_rows(c, x, nullptr, 1 << 30, K, w.wf, w.b, resid, w.w.N, out, w.w.N, S, w.w.N, K, act);
     };
+    c->skip_scope = true;  // (timing experiments: alm_set_option debug_skip drops kernel classes inside the layers)
     for (int l = 0; l < 4; ++l) {
       const DecLayerW& w = m->dec[d][l];
       const long dl = static_cast<long>(d) * 4 + l;
@@ -487,7 +493,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
         cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial, u.xq_counters,
+                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
                       nullptr, nullptr, u.of);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
@@ -499,6 +505,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       lin(u.lnf, 512, w.l1, ACT_RELU, u.hidf, nullptr);
       lin(u.hidf, 2048, w.l2, ACT_NONE, u.x, u.x);
     }
+    c->skip_scope = false;
     if (!want_logits) return;
     gather_ln(c, u.x, 512, nullptr, 1, 512, S, m->dec_norm[d].g, m->dec_norm[d].b, 1e-5f, false, nullptr, 0, u.lnf, 512,
               nullptr, nullptr, 512, nullptr, nullptr);
@@ -507,6 +514,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     lin(u.h1f, 512, m->head[d][2], ACT_NONE, u.logits, nullptr);
     return;
   }
+  c->skip_scope = true;
   for (int l = 0; l < 4; ++l) {
     const DecLayerW& w = m->dec[d][l];
     const long dl = static_cast<long>(d) * 4 + l;
@@ -527,7 +535,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
         cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial, u.xq_counters,
+                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
                       u.o.hi, u.o.lo, nullptr);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
@@ -539,7 +547,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       cross_attn_mq(c, u.q.hi, u.q.lo, nullptr, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff,
-                    m->vt_lo + voff, m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_splits, u.mq_bps, u.xq_partial,
+                    m->vt_lo + voff, m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial,
                     u.xq_counters, u.o.hi, u.o.lo, nullptr);
     } else {
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
@@ -574,6 +582,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     linear(c, u.ln, S, w.l1, ACT_RELU, nullptr, &u.hid);
     linear(c, u.hid, S, w.l2, ACT_NONE, u.x, nullptr, u.x, nullptr, nullptr, 512);
   }
+  c->skip_scope = false;
   if (!want_logits) return;
   gather_ln(c, u.x, 512, nullptr, 1, 512, S, m->dec_norm[d].g, m->dec_norm[d].b, 1e-5f, false, nullptr, 0, nullptr, 0,
             u.ln.hi, u.ln.lo, 512, nullptr, nullptr);
@@ -616,7 +625,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl, c->gemm_grid_cap, c->debug_skip, c->xattn_ctas_per_sm, c->sattn_wide};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {
@@ -667,6 +676,34 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   ws.release(m->ws_mark);
   HeadCfg hc{cfg.num_bins, cfg.pt_eos, cfg.rec_eos, cfg.recog_pad, m->vie};
   c->timing_valid[1] = false;
+  // The decode loops optionally run on internal high-priority streams (fork from / join to the caller's stream)
+  struct DecodeScope {
+    Ctx* c;
+    cudaStream_t user;
+    bool swapped;
+    ~DecodeScope() {
+      c->gemm_grid_cap = 0;
+      if (swapped) {
+        cudaStream_t hi = c->stream;
+        c->stream = user;
+        if (cudaEventRecord(c->ev_prio, hi) == cudaSuccess) cudaStreamWaitEvent(user, c->ev_prio, 0);
+      }
+    }
+  } scope{c, c->stream, false};
+  c->gemm_grid_cap = c->dec_grid_cap;
+  if (c->decode_priority) {
+    int least = 0, greatest = 0;
+    ALM_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    if (!c->stream_hi) {
+      ALM_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, greatest));
+      ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
+    }
+    if (!c->stream2) ALM_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest));
+    ALM_CHECK_CUDA(cudaEventRecord(c->ev_prio, c->stream));
+    ALM_CHECK_CUDA(cudaStreamWaitEvent(c->stream_hi, c->ev_prio, 0));
+    c->stream = c->stream_hi;
+    scope.swapped = true;
+  }
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[2], c->stream));
 
   // ------------------------------------------------------------------ pt loop (transformer.py:102-141)

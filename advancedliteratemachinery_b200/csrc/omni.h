@@ -109,11 +109,11 @@ void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo,
                    bf16* out_hi, bf16* out_lo, float* out_f32 = nullptr);
 int cross_attn_q1_splits(Ctx* c, int nimg, int M);
 // fused multi-query cross-attention (xattn.cu): Ncap query rows per image against the cached K_c / V_c^T
-void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* key_splits, int* blocks_per_split, int* pairs);
-size_t cross_attn_mq_partial_floats(int pairs, int key_splits);
+void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_parts, int* pairs);
+size_t cross_attn_mq_partial_floats(int pairs, int max_parts);
 void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
                    const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo, const uint8_t* kpm, int M, int Mpad,
-                   int key_splits, int blocks_per_split, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
+                   int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
                    float* out_f32);
 void add_i32(Ctx* c, int* p, int v);
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,

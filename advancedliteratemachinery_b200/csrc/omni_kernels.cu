@@ -288,6 +288,82 @@ self_attn_step_kernel(const float* __restrict__ qk, const float* __restrict__ vn
   }
 }
 
+// Same step for FEW sequences (the pt loop: one per image): one CTA of 4 warps per (sequence, head) so that the
+// t+1 cached positions are spread over 128 threads instead of one warp -- the step is pure latency.
+__global__ void __launch_bounds__(128)
+self_attn_step_wide_kernel(const float* __restrict__ qk, const float* __restrict__ vnew, float* __restrict__ kc,
+                           float* __restrict__ vc, int S, const int* __restrict__ tptr, int Tmax, bf16* __restrict__ out_hi,
+                           bf16* __restrict__ out_lo, float* __restrict__ out_f32, int ld_qk, int ld_v) {
+  extern __shared__ __align__(16) float sw[];  // [Tmax] scores / probabilities, then [8][64] partial outputs
+  __shared__ __align__(16) float sq[64];
+  __shared__ float red[4];
+  const int t = *tptr;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x >> 3, h = blockIdx.x & 7;
+  float* p = sw;
+  float* part = sw + ((Tmax + 3) & ~3);
+  const long cbase = static_cast<long>(s) * Tmax * 512 + h * 64;
+  const float* qrow = qk + static_cast<long>(s) * ld_qk + h * 64;
+  if (tid < 64) {  // append k, v of the new position; stage q / 8
+    kc[cbase + static_cast<long>(t) * 512 + tid] = qrow[512 + tid];
+    vc[cbase + static_cast<long>(t) * 512 + tid] = vnew[static_cast<long>(s) * ld_v + h * 64 + tid];
+    sq[tid] = qrow[tid] * 0.125f;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = tid; j <= t; j += 128) {
+    const float* kj = kc + cbase + static_cast<long>(j) * 512;
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(kj + d);
+      const float4 qq = *reinterpret_cast<const float4*>(sq + d);
+      a = fmaf(qq.x, kk.x, a); a = fmaf(qq.y, kk.y, a); a = fmaf(qq.z, kk.z, a); a = fmaf(qq.w, kk.w, a);
+    }
+    p[j] = a;
+    m = fmaxf(m, a);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j <= t; j += 128) {
+    const float e = expf(p[j] - m);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = (red[0] + red[1]) + (red[2] + red[3]);
+  // P.V: 8 position groups x 16 threads (4 dims each); every V row is one coalesced 256-byte read
+  const int jg = tid >> 4, dq = (tid & 15) * 4;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int j = jg; j <= t; j += 8) {
+    const float pj = p[j] / sum;
+    const float4 v = *reinterpret_cast<const float4*>(vc + cbase + static_cast<long>(j) * 512 + dq);
+    o.x = fmaf(pj, v.x, o.x); o.y = fmaf(pj, v.y, o.y); o.z = fmaf(pj, v.z, o.z); o.w = fmaf(pj, v.w, o.w);
+  }
+  *reinterpret_cast<float4*>(part + jg * 64 + dq) = o;
+  __syncthreads();
+  if (tid < 64) {
+    float y = 0.f;
+#pragma unroll
+    for (int gidx = 0; gidx < 8; ++gidx) y += part[gidx * 64 + tid];
+    const long oo = static_cast<long>(s) * 512 + h * 64 + tid;
+    if (out_f32) out_f32[oo] = y;
+    if (out_hi) {
+      bf16 hh, ll;
+      split_bf16(y, hh, ll);
+      out_hi[oo] = hh;
+      if (out_lo) out_lo[oo] = ll;
+    }
+  }
+}
+
 // Fused single-query cross-attention for the pt loop (one live sequence per image, transformer.py:444-447):
 // scores = (q / 8) . K_c^T over the M memory tokens of the image, key-padding mask, softmax, P . V_c -- without
 // materialising the [S*8, M] score / probability matrices.  K_c / V_c^T are the cached split-bf16 projections
@@ -603,7 +679,16 @@ void embed_ln(Ctx* c, const int* tokens, int tstride, const int* tptr, int S, co
 }
 void self_attn_step(Ctx* c, const float* qk, const float* vnew, float* kc, float* vc, int S, const int* t, int Tmax,
                     bf16* out_hi, bf16* out_lo, float* out_f32, int ld_qk, int ld_v) {
+  if (c->skipped(8)) return;
   const long groups = static_cast<long>(S) * 8;
+  if (groups <= 4L * c->num_sms && c->sattn_wide) {  // few sequences: a whole CTA per (sequence, head)
+    const size_t sm = (static_cast<size_t>((Tmax + 3) & ~3) + 8 * 64) * sizeof(float);
+    ALM_PIN_CARVEOUT(self_attn_step_wide_kernel);
+    self_attn_step_wide_kernel<<<static_cast<unsigned>(groups), 128, sm, c->stream>>>(qk, vnew, kc, vc, S, t, Tmax, out_hi,
+                                                                                   out_lo, out_f32, ld_qk, ld_v);
+    count_launch(c); check_launch("self_attn_step_wide");
+    return;
+  }
   const size_t sm = static_cast<size_t>(4) * Tmax * sizeof(float);
   ALM_PIN_CARVEOUT(self_attn_step_kernel);
   self_attn_step_kernel<<<static_cast<unsigned>((groups + 3) / 4), 128, sm, c->stream>>>(qk, vnew, kc, vc, S, t, Tmax,
@@ -627,6 +712,7 @@ void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_promp
 void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo,
                    const uint8_t* kpm, int nimg, int M, int Mpad, float* partial, int* counters, int nsplit,
                    bf16* out_hi, bf16* out_lo, float* out_f32) {
+  if (c->skipped(1)) return;
   int kps = (M + nsplit - 1) / nsplit;
   kps = (kps + 7) & ~7;
   const size_t sm = static_cast<size_t>(kps) * sizeof(float);

@@ -8,13 +8,14 @@
 // half a tcgen05 instruction's rows, so the warp-level MMA is the right granularity (see kernels.cu, window
 // attention).  HBM floor: K_c + V_c of one decoder layer are streamed once per layer-step.
 //
-//   grid (nimg * 8 * nqb, key_splits); 4 warps, warp w owns query rows 16w..16w+15 of the block.
+//   Persistent grid (2 CTAs per SM); the (image, head, query block) x key-block work list is cut into equal
+//   contiguous runs, one per CTA.  4 warps, warp w owns query rows 16w..16w+15 of the block.
 //   Q16 variant (<= 16 sequences per image: the pt loop has ONE): all four warps share the single 16-row query
 //   tile and split every 64-key block four ways (16 keys each), so the MMA work drops 4x and the kernel is purely
 //   HBM-bound on the K_c / V_c^T stream; each warp publishes its own (m, l, o) partial.
 //   Key blocks of 64 are staged with cp.async into a 2-stage ring (hi/lo planes of K [key][dim] and V^T [dim][key],
-//   144-byte pitch -> conflict-free ldmatrix).  Split partials (m, l, o[64]) are merged by the last CTA of each
-//   (image, head, query block) through a self-resetting counter, so one launch suffices.
+//   144-byte pitch -> conflict-free ldmatrix).  When a run boundary cuts an (image, head, query block), the CTAs
+//   sharing it publish partials (m, l, o[64]) and the last one to arrive merges them (self-resetting counter).
 #include <algorithm>
 
 #include "mma.cuh"
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(128, 3)
 cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, const float* __restrict__ q_f32, int Ncap,
                      const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo, const bf16* __restrict__ vt_hi,
                      const bf16* __restrict__ vt_lo, const uint8_t* __restrict__ kpm, int M, int Mpad, int nqb,
-                     int blocks_per_split, float* __restrict__ partial, int* __restrict__ counters,
+                     int npairs, int max_parts, float* __restrict__ partial, int* __restrict__ counters,
                      bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
   constexpr int NJ = Q16 ? 2 : 8;    // 8-key n-tiles of a block this warp scores
   constexpr int NKK = Q16 ? 1 : 4;   // 16-key k-steps of a block this warp feeds into P.V
@@ -45,17 +46,60 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   uint8_t* smask = mq_smem + MQ_STAGES * MQ_STAGE * 2;
   __shared__ int last_flag;
 
-  const int pair = blockIdx.x, qb = pair % nqb, ih = pair / nqb, h = ih & 7, img = ih >> 3;
-  const int split = blockIdx.y, gs = gridDim.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nkb = (M + MQ_KB - 1) / MQ_KB;
-  const int kb0 = split * blocks_per_split, kb1 = min(nkb, kb0 + blocks_per_split);
+  // ---- persistent, balanced schedule: the npairs x nkb key blocks are cut into gridDim.x equal contiguous runs;
+  //      a run may cover the tail of one (image, head, query block) and the head of the next (two segments)
+  const long NB = static_cast<long>(npairs) * nkb, G = gridDim.x;
+  auto owner = [&](long b) { return static_cast<int>(((b + 1) * G - 1) / NB); };  // CTA whose run contains block b
+  const long b_end = (static_cast<long>(blockIdx.x) + 1) * NB / G;
+  for (long b = static_cast<long>(blockIdx.x) * NB / G; b < b_end;) {
+  const int pair = static_cast<int>(b / nkb), qb = pair % nqb, ih = pair / nqb, h = ih & 7, img = ih >> 3;
+  const int kb0 = static_cast<int>(b - static_cast<long>(pair) * nkb);
+  const int kb1 = static_cast<int>(min(static_cast<long>(nkb), kb0 + (b_end - b)));
+  b += kb1 - kb0;
+  const int first = owner(static_cast<long>(pair) * nkb);
+  const int gs = owner(static_cast<long>(pair) * nkb + nkb - 1) - first + 1;  // CTAs sharing this pair
+  const int split = static_cast<int>(blockIdx.x) - first;
   const int q0 = qb * 64;
   const int j0 = Q16 ? 2 * warp : 0, kk0 = Q16 ? warp : 0;
   const int r_lo = (Q16 ? 0 : warp * 16) + g, r_hi = r_lo + 8;  // the two query rows (within the block) this lane holds
   const bool live_lo = q0 + r_lo < Ncap, live_hi = q0 + r_hi < Ncap;
 
-  // ---- A fragments of q (hi, lo) for the four 16-dim k-steps, straight from global memory (read once)
+  const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;           // K_c[img][dl(base)][h][key][64]
+  const long vbase = (static_cast<long>(img) * 6144 + h * 64) * Mpad;      // V_c^T[img][dl(base)*512 + h*64 + dim][key]
+  auto load_block = [&](int kb, int stage) {
+    bf16* st = tiles + stage * MQ_STAGE;
+    const int key0 = kb * MQ_KB;
+#pragma unroll
+    for (int i = tid; i < 512; i += 128) {
+      const int r = i >> 3, ch = (i & 7) * 8;
+      {  // K row r = key, 8 dims per 16-byte chunk; keys >= M are zero-filled
+        const int key = key0 + r;
+        const bool ok = key < M;
+        const long src = kbase + static_cast<long>(ok ? key : 0) * 64 + ch;
+        cp_async16(st + r * MQ_PITCH + ch, kc_hi + src, ok ? 16 : 0);
+        if (NS == 3) cp_async16(st + MQ_PLANE + r * MQ_PITCH + ch, kc_lo + src, ok ? 16 : 0);
+      }
+      {  // V^T row r = dim, 8 keys per chunk; chunks at or beyond Mpad are zero-filled (Mpad % 8 == 0; the pad
+         // columns M..Mpad-1 are kept zero by the encoder)
+        const int key = key0 + ch;
+        const bool ok = key < Mpad;
+        const long src = vbase + static_cast<long>(r) * Mpad + (ok ? key : 0);
+        cp_async16(st + 2 * MQ_PLANE + r * MQ_PITCH + ch, vt_hi + src, ok ? 16 : 0);
+        if (NS == 3) cp_async16(st + 3 * MQ_PLANE + r * MQ_PITCH + ch, vt_lo + src, ok ? 16 : 0);
+      }
+    }
+    if (tid < MQ_KB) {
+      const int key = key0 + tid;
+      smask[stage * MQ_KB + tid] = (key < M) ? (kpm ? kpm[static_cast<long>(img) * M + key] : 0) : 1;
+    }
+  };
+
+  load_block(kb0, 0);  // first key block in flight while the query fragments are fetched
+  cp_async_commit();
+
+  // ---- A fragments of q (hi, lo) for the four 16-dim k-steps, straight from global memory (read once per segment)
   constexpr int NP = (NS == 3) ? 2 : 1;
   uint32_t aq[NP][4][4];
   {
@@ -93,46 +137,12 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
     }
   }
 
-  const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;           // K_c[img][dl(base)][h][key][64]
-  const long vbase = (static_cast<long>(img) * 6144 + h * 64) * Mpad;      // V_c^T[img][dl(base)*512 + h*64 + dim][key]
-  auto load_block = [&](int kb, int stage) {
-    bf16* st = tiles + stage * MQ_STAGE;
-    const int key0 = kb * MQ_KB;
-#pragma unroll
-    for (int i = tid; i < 512; i += 128) {
-      const int r = i >> 3, ch = (i & 7) * 8;
-      {  // K row r = key, 8 dims per 16-byte chunk; keys >= M are zero-filled
-        const int key = key0 + r;
-        const bool ok = key < M;
-        const long src = kbase + static_cast<long>(ok ? key : 0) * 64 + ch;
-        cp_async16(st + r * MQ_PITCH + ch, kc_hi + src, ok ? 16 : 0);
-        if (NS == 3) cp_async16(st + MQ_PLANE + r * MQ_PITCH + ch, kc_lo + src, ok ? 16 : 0);
-      }
-      {  // V^T row r = dim, 8 keys per chunk; chunks at or beyond Mpad are zero-filled (Mpad % 8 == 0; the pad
-         // columns M..Mpad-1 are kept zero by the encoder)
-        const int key = key0 + ch;
-        const bool ok = key < Mpad;
-        const long src = vbase + static_cast<long>(r) * Mpad + (ok ? key : 0);
-        cp_async16(st + 2 * MQ_PLANE + r * MQ_PITCH + ch, vt_hi + src, ok ? 16 : 0);
-        if (NS == 3) cp_async16(st + 3 * MQ_PLANE + r * MQ_PITCH + ch, vt_lo + src, ok ? 16 : 0);
-      }
-    }
-    if (tid < MQ_KB) {
-      const int key = key0 + tid;
-      smask[stage * MQ_KB + tid] = (key < M) ? (kpm ? kpm[static_cast<long>(img) * M + key] : 0) : 1;
-    }
-  };
-
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
   float o[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   const int lrow = lane & 7, lcol = (lane >> 3) * 8;  // ldmatrix.x4: row within the 8-row group, 8-column chunk
 
-  if (kb0 < kb1) {
-    load_block(kb0, 0);
-    cp_async_commit();
-  }
   for (int kb = kb0; kb < kb1; ++kb) {
     const int stage = (kb - kb0) & 1;
     if (kb + 1 < kb1) {
@@ -277,7 +287,7 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
         if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + ob_hi + 8 * n) = ll;
       }
     }
-    return;
+    continue;
   }
   // ---- publish (m, l, o[64]) per query row and partial; the last CTA of the pair merges.  A partial is one key
   //      split (64 rows) or, for Q16, one warp of one key split (16 rows).
@@ -285,8 +295,8 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   const int nparts = Q16 ? gs * 4 : gs;
   {
     const int part = Q16 ? split * 4 + warp : split;
-    float* p_lo = partial + ((static_cast<long>(pair) * nparts + part) * PR + r_lo) * MQ_PART;
-    float* p_hi = partial + ((static_cast<long>(pair) * nparts + part) * PR + r_hi) * MQ_PART;
+    float* p_lo = partial + ((static_cast<long>(pair) * max_parts * 64) + part * PR + r_lo) * MQ_PART;
+    float* p_hi = partial + ((static_cast<long>(pair) * max_parts * 64) + part * PR + r_hi) * MQ_PART;
     if (t == 0) {
       p_lo[0] = m_lo; p_lo[1] = l_lo;
       p_hi[0] = m_hi; p_hi[1] = l_hi;
@@ -301,13 +311,13 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   __syncthreads();
   if (tid == 0) last_flag = (atomicAdd(&counters[pair], 1) == gs - 1);
   __syncthreads();
-  if (!last_flag) return;
+  if (!last_flag) continue;
   __threadfence();
   {
     constexpr int DPT = Q16 ? 8 : 32;         // dims per merging thread
     const int row = Q16 ? tid >> 3 : tid >> 1, half = Q16 ? (tid & 7) * 8 : (tid & 1) * 32;
     if (q0 + row < Ncap) {
-      const float* base = partial + (static_cast<long>(pair) * nparts * PR + row) * MQ_PART;
+      const float* base = partial + (static_cast<long>(pair) * max_parts * 64 + row) * MQ_PART;
       const long sstride = static_cast<long>(PR) * MQ_PART;
       float mm = -INFINITY;
       for (int sidx = 0; sidx < nparts; ++sidx) mm = fmaxf(mm, base[sidx * sstride]);
@@ -347,31 +357,35 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
     }
   }
   if (tid == 0) counters[pair] = 0;  // ready for the next launch (graph replay)
+  }  // segments of this CTA's run
 }
 
 }  // namespace
 
-// Split plan: ~3 resident CTAs per SM (the kernel's occupancy), at least two key blocks per CTA.
-void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* key_splits, int* blocks_per_split, int* pairs) {
+// Launch plan: a persistent grid of `ctas_per_sm` CTAs per SM (default 2: 148 KB of the SM's shared memory, so the
+// small kernels of the other in-flight decode streams still find room next to this HBM-bound one), never more
+// CTAs than key blocks.
+void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_parts, int* pairs) {
   const int nqb = (Ncap + 63) / 64;
   const int np = nimg * 8 * nqb;
   const int nkb = (M + MQ_KB - 1) / MQ_KB;
-  int gs = std::max(1, (3 * c->num_sms) / np);
-  gs = std::min(gs, std::max(1, nkb / 2));
-  const int bps = (nkb + gs - 1) / gs;
-  *key_splits = (nkb + bps - 1) / bps;
-  *blocks_per_split = bps;
+  const long NB = static_cast<long>(np) * nkb;
+  const int G = static_cast<int>(std::min<long>(NB, static_cast<long>(c->num_sms) * std::max(1, c->xattn_ctas_per_sm)));
+  const int bpc = static_cast<int>(NB / G);  // >= 1 key blocks in every run
+  *grid = G;
+  *max_parts = (nkb + bpc - 1) / bpc + 1;
   *pairs = np;
 }
 
-size_t cross_attn_mq_partial_floats(int pairs, int key_splits) {
-  return static_cast<size_t>(pairs) * key_splits * 64 * MQ_PART;  // Q16: 4 warps x 16 rows per split -- same size
+size_t cross_attn_mq_partial_floats(int pairs, int max_parts) {
+  return static_cast<size_t>(pairs) * max_parts * 64 * MQ_PART;  // Q16: 4 warps x 16 rows per part -- same size
 }
 
 void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
                    const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo, const uint8_t* kpm, int M, int Mpad,
-                   int key_splits, int blocks_per_split, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
+                   int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
                    float* out_f32) {
+  if (c->skipped(1)) return;
   const int nqb = (Ncap + 63) / 64;
   static bool attr = false;
   if (!attr) {
@@ -388,10 +402,10 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
   const bool q16 = Ncap <= 16;
   ALM_REQUIRE(q16 || (out_hi && !out_f32), ALM_ERR_INVALID, "cross_attn_mq: fp32 output only on the <= 16-query path");
   const bool three = c->nsplit == 3 && (q_f32 || q_lo) && kc_lo && vt_lo;
-  dim3 grid(nimg * 8 * nqb, key_splits);
+  const int npairs = nimg * 8 * nqb;
 #define ALM_MQ_LAUNCH(NS, Q)                                                                                            \
   cross_attn_mq_kernel<NS, Q><<<grid, 128, MQ_SMEM, c->stream>>>(q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vt_hi, vt_lo, kpm, \
-                                                                 M, Mpad, nqb, blocks_per_split, partial, counters,     \
+                                                                 M, Mpad, nqb, npairs, max_parts, partial, counters,    \
                                                                  out_hi, out_lo, out_f32)
   if (three) { if (q16) ALM_MQ_LAUNCH(3, true); else ALM_MQ_LAUNCH(3, false); }
   else       { if (q16) ALM_MQ_LAUNCH(1, true); else ALM_MQ_LAUNCH(1, false); }

@@ -388,3 +388,13 @@ def test_fused_cross_attention_matches_gemm_path_and_oracle():
         k = min(n, 8)
         assert _maxrel(lg[0][:k], ref[:k]) < LOGIT_REL_TOL
         assert _rel(lg[0][:k], ref[:k]) < 1e-4
+        # the two self-attention step kernels (CTA per (sequence, head) for few sequences / warp per pair) and the
+        # fused kernel's 2 vs 3 CTAs per SM schedules agree as well
+        try:
+            m.ctx.set_option('sattn_wide', 0)
+            m.ctx.set_option('xattn_ctas_per_sm', 3)
+            alt = m.decode_logits(0, 'rec', seq[:n])
+        finally:
+            m.ctx.set_option('sattn_wide', 1)
+            m.ctx.set_option('xattn_ctas_per_sm', 2)
+        assert _maxrel(lg[0], alt) < 2e-5, (n, _maxrel(lg[0], alt))
