@@ -255,8 +255,13 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   m->kpm = ws.get<uint8_t>(BM);
   m->kc_hi = ws.get<bf16>(BM * 6144);
   m->kc_lo = ws.get<bf16>(BM * 6144);
-  m->vt_hi = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
-  m->vt_lo = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
+  m->vc_hi = ws.get<bf16>(BM * 6144);
+  m->vc_lo = ws.get<bf16>(BM * 6144);
+  m->vt_hi = m->vt_lo = nullptr;
+  if (c->xattn_impl == 1) {  // the unfused debug path multiplies P by a feature-major V_c^T
+    m->vt_hi = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
+    m->vt_lo = ws.get<bf16>(static_cast<size_t>(B) * 6144 * m->Mpad);
+  }
   m->ws_mark = ws.mark();
 
   // ---- patch embed: im2col -> GEMM(+bias) -> LN   (swin_transformer.py:427-443)
@@ -372,11 +377,19 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
     gemm(c, a, w, e);
   }
-  if (m->Mpad != m->M) {  // pad columns M..Mpad-1 of V_c^T must be finite zeros: the fused attention multiplies them by p = 0
-    ALM_CHECK_CUDA(cudaMemsetAsync(m->vt_hi, 0, static_cast<size_t>(B) * 6144 * m->Mpad * sizeof(bf16), c->stream));
-    ALM_CHECK_CUDA(cudaMemsetAsync(m->vt_lo, 0, static_cast<size_t>(B) * 6144 * m->Mpad * sizeof(bf16), c->stream));
+  {  // V_c[b][dl][h][m][64] = memory Wv^T + bv, same head-major layout: a 64-key block of one (image, layer, head) is
+     // one contiguous 8 KB run per plane, which is what the fused attention streams
+    Operand a = act_op(mem.hi, mem.lo, m->M, 512, 512);
+    a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
+    Operand w = m->ca_v_all.w.op();
+    w.rows = 64; w.nb0 = 96; w.bs0 = static_cast<long>(64) * 512;
+    Epilogue e;
+    e.out_hi = m->vc_hi; e.out_lo = m->vc_lo; e.ldo = 64;
+    e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
+    e.bias = m->ca_v_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
+    gemm(c, a, w, e);
   }
-  {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
+  if (m->vt_hi) {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
     Operand bop = act_op(mem.hi, mem.lo, m->M, 512, 512);
     bop.nb1 = B; bop.bs1 = static_cast<long>(m->M) * 512;
     Epilogue e;
@@ -492,8 +505,8 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
-        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
+        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff, m->vc_lo + koff,
+                      m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
                       nullptr, nullptr, u.of);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
@@ -534,8 +547,8 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
-        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
-                      m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
+        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff, m->vc_lo + koff,
+                      m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
                       u.o.hi, u.o.lo, nullptr);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
@@ -545,9 +558,8 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       // Ncap queries per image: scores, mask, online softmax and P.V fused; K_c / V_c^T streamed once per layer-step
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
-      const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
-      cross_attn_mq(c, u.q.hi, u.q.lo, nullptr, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff,
-                    m->vt_lo + voff, m->kpm + static_cast<long>(img0) * M, M, Mpad, u.mq_grid, u.mq_parts, u.xq_partial,
+      cross_attn_mq(c, u.q.hi, u.q.lo, nullptr, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff,
+                    m->vc_lo + koff, m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial,
                     u.xq_counters, u.o.hi, u.o.lo, nullptr);
     } else {
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
@@ -664,6 +676,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
                       int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode before alm_omni_encode");
+  ALM_REQUIRE(c->xattn_impl == 0 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
   ALM_REQUIRE(n_prompt >= 1 && n_prompt <= 16, ALM_ERR_INVALID, "pt prompt length");
   ALM_REQUIRE(cfg.pt_seq_length >= 1 && n_prompt + cfg.pt_seq_length - 1 <= 1024, ALM_ERR_INVALID,
               "prompt + pt_seq_length exceeds the 1024-row position table (transformer.py:475)");
@@ -879,6 +892,7 @@ void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_d
 void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode_logits before alm_omni_encode");
+  ALM_REQUIRE(c->xattn_impl == 0 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
   ALM_REQUIRE(image >= 0 && image < m->B && kind >= 0 && kind < 3 && n_seq > 0 && len > 0 && len <= 1024,
               ALM_ERR_INVALID, "decode_logits arguments");
   Arena& ws = c->ws;

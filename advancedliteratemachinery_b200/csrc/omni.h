@@ -70,7 +70,8 @@ struct OmniModel {
   float* pos = nullptr;                                   // [B*M,512]
   uint8_t* kpm = nullptr;                                 // [B*M]
   bf16 *kc_hi = nullptr, *kc_lo = nullptr;                // [B, 12 (dec,layer), 8 heads, M, 64]
-  bf16 *vt_hi = nullptr, *vt_lo = nullptr;                // [B, 6144, Mpad]
+  bf16 *vc_hi = nullptr, *vc_lo = nullptr;                // [B, 12 (dec,layer), 8 heads, M, 64]
+  bf16 *vt_hi = nullptr, *vt_lo = nullptr;                // [B, 6144, Mpad] (only for the unfused debug path, xattn_impl 1)
   size_t ws_mark = 0;                                     // arena offset after the encode-persistent buffers
   // captured decode-step graphs, keyed by everything that determines the launch sequence and its pointers
   struct StepGraph { cudaGraphExec_t exec; long launches; };
@@ -112,7 +113,7 @@ int cross_attn_q1_splits(Ctx* c, int nimg, int M);
 void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_parts, int* pairs);
 size_t cross_attn_mq_partial_floats(int pairs, int max_parts);
 void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
-                   const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo, const uint8_t* kpm, int M, int Mpad,
+                   const bf16* kc_lo, const bf16* vc_hi, const bf16* vc_lo, const uint8_t* kpm, int M,
                    int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
                    float* out_f32);
 void add_i32(Ctx* c, int* p, int v);

@@ -1,7 +1,7 @@
 // Fused multi-query cross-attention for the batched poly / rec decode loops (transformer.py:444-447 with
 // Ncap live sequences per image): per (image, head, 64-query block)
 //     S = (q / 8) K_c^T  ->  key-padding mask  ->  online softmax  ->  O = P V_c
-// in ONE pass over the cached split-bf16 K_c / V_c^T of the image, flash-attention style: the [S*8, M] score and
+// in ONE pass over the cached split-bf16 K_c / V_c of the image, flash-attention style: the [S*8, M] score and
 // probability matrices never touch HBM (they were 4 x 134 MB per layer-step at 16 pages x 64 instances).
 // Both products run on mma.sync.m16n8k16 with the three-term split hi*hi + lo*hi + hi*lo accumulated in fp32 --
 // the same fp32-class scheme as the GEMM engine; softmax statistics stay in fp32 registers.  64-query tiles are
@@ -13,7 +13,7 @@
 //   Q16 variant (<= 16 sequences per image: the pt loop has ONE): all four warps share the single 16-row query
 //   tile and split every 64-key block four ways (16 keys each), so the MMA work drops 4x and the kernel is purely
 //   HBM-bound on the K_c / V_c^T stream; each warp publishes its own (m, l, o) partial.
-//   Key blocks of 64 are staged with cp.async into a 2-stage ring (hi/lo planes of K [key][dim] and V^T [dim][key],
+//   Key blocks of 64 are staged with cp.async into a 2-stage ring (hi/lo planes of K and V, both [key][dim],
 //   144-byte pitch -> conflict-free ldmatrix).  When a run boundary cuts an (image, head, query block), the CTAs
 //   sharing it publish partials (m, l, o[64]) and the last one to arrive merges them (self-resetting counter).
 #include <algorithm>
@@ -35,8 +35,8 @@ constexpr int MQ_PART = 66;                   // floats per partial row: m, l, o
 template <int NS, bool Q16>
 __global__ void __launch_bounds__(128, 3)
 cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, const float* __restrict__ q_f32, int Ncap,
-                     const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo, const bf16* __restrict__ vt_hi,
-                     const bf16* __restrict__ vt_lo, const uint8_t* __restrict__ kpm, int M, int Mpad, int nqb,
+                     const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo, const bf16* __restrict__ vc_hi,
+                     const bf16* __restrict__ vc_lo, const uint8_t* __restrict__ kpm, int M, int nqb,
                      int npairs, int max_parts, float* __restrict__ partial, int* __restrict__ counters,
                      bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
   constexpr int NJ = Q16 ? 2 : 8;    // 8-key n-tiles of a block this warp scores
@@ -66,29 +66,23 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   const int r_lo = (Q16 ? 0 : warp * 16) + g, r_hi = r_lo + 8;  // the two query rows (within the block) this lane holds
   const bool live_lo = q0 + r_lo < Ncap, live_hi = q0 + r_hi < Ncap;
 
-  const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;           // K_c[img][dl(base)][h][key][64]
-  const long vbase = (static_cast<long>(img) * 6144 + h * 64) * Mpad;      // V_c^T[img][dl(base)*512 + h*64 + dim][key]
+  const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;  // K_c / V_c [img][dl(base)][h][key][64]
   auto load_block = [&](int kb, int stage) {
     bf16* st = tiles + stage * MQ_STAGE;
     const int key0 = kb * MQ_KB;
 #pragma unroll
     for (int i = tid; i < 512; i += 128) {
+      // row r = key, 8 dims per 16-byte chunk; a warp instruction covers 4 consecutive keys = 512 contiguous bytes,
+      // the whole block 8 KB contiguous per plane; keys >= M are zero-filled
       const int r = i >> 3, ch = (i & 7) * 8;
-      {  // K row r = key, 8 dims per 16-byte chunk; keys >= M are zero-filled
-        const int key = key0 + r;
-        const bool ok = key < M;
-        const long src = kbase + static_cast<long>(ok ? key : 0) * 64 + ch;
-        cp_async16(st + r * MQ_PITCH + ch, kc_hi + src, ok ? 16 : 0);
-        if (NS == 3) cp_async16(st + MQ_PLANE + r * MQ_PITCH + ch, kc_lo + src, ok ? 16 : 0);
-      }
-      {  // V^T row r = dim, 8 keys per chunk; chunks at or beyond Mpad are zero-filled (Mpad % 8 == 0; the pad
-         // columns M..Mpad-1 are kept zero by the encoder)
-        const int key = key0 + ch;
-        const bool ok = key < Mpad;
-        const long src = vbase + static_cast<long>(r) * Mpad + (ok ? key : 0);
-        cp_async16(st + 2 * MQ_PLANE + r * MQ_PITCH + ch, vt_hi + src, ok ? 16 : 0);
-        if (NS == 3) cp_async16(st + 3 * MQ_PLANE + r * MQ_PITCH + ch, vt_lo + src, ok ? 16 : 0);
-      }
+      const int key = key0 + r;
+      const bool ok = key < M;
+      const long src = kbase + static_cast<long>(ok ? key : 0) * 64 + ch;
+      const int nb = ok ? 16 : 0;
+      cp_async16(st + r * MQ_PITCH + ch, kc_hi + src, nb);
+      if (NS == 3) cp_async16(st + MQ_PLANE + r * MQ_PITCH + ch, kc_lo + src, nb);
+      cp_async16(st + 2 * MQ_PLANE + r * MQ_PITCH + ch, vc_hi + src, nb);
+      if (NS == 3) cp_async16(st + 3 * MQ_PLANE + r * MQ_PITCH + ch, vc_lo + src, nb);
     }
     if (tid < MQ_KB) {
       const int key = key0 + tid;
@@ -225,41 +219,22 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
       split_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[kk][2], pl[kk][2]);
       split_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[kk][3], pl[kk][3]);
     }
-    if (Q16) {
-      // this warp's 16 keys only: one ldmatrix.x4 covers (b0, b1) of two consecutive dim tiles
+    // v tiles are [key][dim]: the B fragments come through ldmatrix.trans; matrix i of an x4 load = (key half i & 1,
+    // dim tile 2 * np + (i >> 1)), i.e. (b0, b1) of two consecutive 8-dim output tiles for one 16-key step
+#pragma unroll
+    for (int kk = 0; kk < NKK; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         uint32_t vh[4], vl[4];
-        const int roff = (8 * (2 * np + (lane >> 4)) + lrow) * MQ_PITCH + 16 * kk0 + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4(vh, sVh + roff);
-        if (NS == 3) ldmatrix_x4(vl, sVl + roff);
+        const int roff = (16 * (kk0 + kk) + ((lane >> 3) & 1) * 8 + lrow) * MQ_PITCH + (2 * np + (lane >> 4)) * 8;
+        ldmatrix_x4_trans(vh, sVh + roff);
+        if (NS == 3) ldmatrix_x4_trans(vl, sVl + roff);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          mma_bf16_16816(o[2 * np + q], ph[0], vh[2 * q], vh[2 * q + 1]);
+          mma_bf16_16816(o[2 * np + q], ph[kk], vh[2 * q], vh[2 * q + 1]);
           if (NS == 3) {
-            mma_bf16_16816(o[2 * np + q], pl[0], vh[2 * q], vh[2 * q + 1]);
-            mma_bf16_16816(o[2 * np + q], ph[0], vl[2 * q], vl[2 * q + 1]);
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        uint32_t vh[2][4], vl[2][4];
-        const int roff = (8 * n + lrow) * MQ_PITCH + lcol;
-        ldmatrix_x4(vh[0], sVh + roff);
-        ldmatrix_x4(vh[1], sVh + roff + 32);
-        if (NS == 3) {
-          ldmatrix_x4(vl[0], sVl + roff);
-          ldmatrix_x4(vl[1], sVl + roff + 32);
-        }
-#pragma unroll
-        for (int kk = 0; kk < NKK; ++kk) {
-          const uint32_t b0 = vh[kk >> 1][(kk & 1) * 2], b1 = vh[kk >> 1][(kk & 1) * 2 + 1];
-          mma_bf16_16816(o[n], ph[kk], b0, b1);
-          if (NS == 3) {
-            mma_bf16_16816(o[n], pl[kk], b0, b1);
-            mma_bf16_16816(o[n], ph[kk], vl[kk >> 1][(kk & 1) * 2], vl[kk >> 1][(kk & 1) * 2 + 1]);
+            mma_bf16_16816(o[2 * np + q], pl[kk], vh[2 * q], vh[2 * q + 1]);
+            mma_bf16_16816(o[2 * np + q], ph[kk], vl[2 * q], vl[2 * q + 1]);
           }
         }
       }
@@ -382,7 +357,7 @@ size_t cross_attn_mq_partial_floats(int pairs, int max_parts) {
 }
 
 void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
-                   const bf16* kc_lo, const bf16* vt_hi, const bf16* vt_lo, const uint8_t* kpm, int M, int Mpad,
+                   const bf16* kc_lo, const bf16* vc_hi, const bf16* vc_lo, const uint8_t* kpm, int M,
                    int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo,
                    float* out_f32) {
   if (c->skipped(1)) return;
@@ -397,15 +372,14 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
     prep(cross_attn_mq_kernel<3, true>); prep(cross_attn_mq_kernel<1, true>);
     attr = true;
   }
-  ALM_REQUIRE((Mpad & 7) == 0, ALM_ERR_INVALID, "cross_attn_mq: Mpad must be a multiple of 8");
   ALM_REQUIRE(q_f32 || q_hi, ALM_ERR_INVALID, "cross_attn_mq: no query operand");
   const bool q16 = Ncap <= 16;
   ALM_REQUIRE(q16 || (out_hi && !out_f32), ALM_ERR_INVALID, "cross_attn_mq: fp32 output only on the <= 16-query path");
-  const bool three = c->nsplit == 3 && (q_f32 || q_lo) && kc_lo && vt_lo;
+  const bool three = c->nsplit == 3 && (q_f32 || q_lo) && kc_lo && vc_lo;
   const int npairs = nimg * 8 * nqb;
 #define ALM_MQ_LAUNCH(NS, Q)                                                                                            \
-  cross_attn_mq_kernel<NS, Q><<<grid, 128, MQ_SMEM, c->stream>>>(q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vt_hi, vt_lo, kpm, \
-                                                                 M, Mpad, nqb, npairs, max_parts, partial, counters,    \
+  cross_attn_mq_kernel<NS, Q><<<grid, 128, MQ_SMEM, c->stream>>>(q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vc_hi, vc_lo, kpm, \
+                                                                 M, nqb, npairs, max_parts, partial, counters,    \
                                                                  out_hi, out_lo, out_f32)
   if (three) { if (q16) ALM_MQ_LAUNCH(3, true); else ALM_MQ_LAUNCH(3, false); }
   else       { if (q16) ALM_MQ_LAUNCH(1, true); else ALM_MQ_LAUNCH(1, false); }

@@ -48,6 +48,17 @@ if os.environ.get('PROBE_SKIP'):
             m.decode()
         print(f'skip={mask:2d}: dec K=1 {run("dec", 1, 2):7.1f}   K=4 {run("dec", 4, 2):7.1f} ms per batch', flush=True)
     sys.exit(0)
+if os.environ.get('PROBE_OPTS'):
+    # decode-only scaling under alternative launch structures
+    for opts in ([], ['use_graphs=0'], ['decode_streams=1'], ['use_graphs=0', 'decode_streams=1']):
+        for m in models:
+            for kv in ('use_graphs=1', 'decode_streams=2'):
+                m.ctx.set_option(kv.split('=')[0], int(kv.split('=')[1]))
+            for kv in opts:
+                m.ctx.set_option(kv.split('=')[0], int(kv.split('=')[1]))
+            m.decode()
+        print(f'{str(opts):40s}: dec K=1 {run("dec", 1, 2):7.1f}   K=2 {run("dec", 2, 2):7.1f}   K=4 {run("dec", 4, 2):7.1f} ms per batch', flush=True)
+    sys.exit(0)
 for kind in ('enc', 'dec', 'all'):
     for K in (1, 2, 3, 4, 6):
         if K > KMAX:
