@@ -46,6 +46,20 @@ def ncu_traffic_bytes():
         return None
 
 
+def pick_inflight(steps):
+    """Contexts in flight for a K-step timed region: steps are pulled from a shared counter, so K steps over C contexts
+    run as rounds of C (the last one possibly partial).  Measured ms per batch with n batches in flight (config 2,
+    tools/concurrency_probe.py): fuller rounds are cheaper, a nearly empty tail round is expensive."""
+    per_batch = {1: 190.0, 2: 165.0, 3: 150.0, 4: 143.0, 5: 141.0, 6: 140.0}
+    best, best_cost = 1, float('inf')
+    for c in range(1, 7):
+        full, tail = divmod(steps, c)
+        cost = full * c * per_batch[c] + (tail * per_batch[tail] if tail else 0.0)
+        if cost < best_cost - 1e-9:
+            best, best_cost = c, cost
+    return best
+
+
 def peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -175,15 +189,16 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--nsplit', type=int, default=3, help='3 = fp32-class split operands (parity mode), 1 = bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--grid-cap', type=int, default=0)
-    ap.add_argument('--inflight', type=int, default=3, help='independent batches in flight per GPU (one context + stream '
-                    'each); the per-token decode loops are latency-bound, so concurrent batches fill the idle SMs')
+    ap.add_argument('--inflight', type=int, default=0, help='independent batches in flight per GPU (one context + stream '
+                    '+ host thread each): the per-token decode loops are latency-bound, concurrent batches fill their '
+                    'launch gaps.  0 = choose 3..6 so that the K timed steps split into equally full rounds')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
     ap.add_argument('--cpu-sample', nargs=2, type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -213,7 +228,7 @@ def main():
     if world > 1:
         sd = broadcast_state_dict(sd, src=0, device=torch.device('cuda', local))
     vocab = OmniVocab(pt_seq_length=2 * N_INST, rec_length=REC_LEN)
-    C_ = max(1, args.inflight)
+    C_ = args.inflight if args.inflight > 0 else pick_inflight(args.steps)
     streams = [torch.cuda.Stream() for _ in range(C_)]
     ctxs, models = [], []
     for j in range(C_):

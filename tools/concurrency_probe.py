@@ -42,7 +42,7 @@ def run(kind, K, reps):
 
 if os.environ.get('PROBE_SKIP'):
     # which kernel class holds the GPU?  decode-only, K = 1 and 4, with one class of layer kernels dropped at a time
-    for mask in (0, 1, 2, 4, 8, 3, 15):
+    for mask in [int(x) for x in os.environ.get('PROBE_MASKS', '0,1,2,4,8,3,15').split(',')]:
         for m in models:
             m.ctx.set_option('debug_skip', mask)
             m.decode()
