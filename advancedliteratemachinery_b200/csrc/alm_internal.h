@@ -179,6 +179,7 @@ struct Ctx {
   int trace_cap = 0;
   unsigned long long* detail_buf = nullptr;  // [64][6] per-role stamps of CTA 0, overwritten by every GEMM (debug)
   int sattn_wide = 1;  // CTA-per-(sequence, head) self-attention step when there are few sequences
+  int xattn_wg = 1;  // 2 = 8-warp variant of the 64-query fused cross-attention (two key groups per block)
   int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
   int xattn_impl = 0;  // 0 = fused flash-style multi-query cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel

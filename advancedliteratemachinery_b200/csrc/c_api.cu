@@ -189,6 +189,9 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "xattn_ctas_per_sm") {
       ALM_REQUIRE(value >= 1 && value <= 3, ALM_ERR_INVALID, "xattn_ctas_per_sm must be 1..3");
       h->c.xattn_ctas_per_sm = static_cast<int>(value);
+    } else if (k == "xattn_wg") {
+      ALM_REQUIRE(value == 1 || value == 2, ALM_ERR_INVALID, "xattn_wg must be 1 or 2");
+      h->c.xattn_wg = static_cast<int>(value);
     } else if (k == "sattn_wide") {
       h->c.sattn_wide = value ? 1 : 0;
     } else if (k == "debug_skip") {

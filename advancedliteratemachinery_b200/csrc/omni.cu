@@ -637,7 +637,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl, c->gemm_grid_cap, c->debug_skip, c->xattn_ctas_per_sm, c->sattn_wide};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl, c->gemm_grid_cap, c->debug_skip, c->xattn_ctas_per_sm, c->sattn_wide, c->xattn_wg};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {

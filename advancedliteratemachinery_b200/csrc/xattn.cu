@@ -10,7 +10,9 @@
 //
 //   Persistent grid (2 CTAs per SM); the (image, head, query block) x key-block work list is cut into equal
 //   contiguous runs, one per CTA.  4 warps, warp w owns query rows 16w..16w+15 of the block.
-//   Q16 variant (<= 16 sequences per image: the pt loop has ONE): all four warps share the single 16-row query
+//   MODE 2 (optional, "xattn_wg" 2): 8 warps -- the four 16-row tiles times two key groups of 32 keys per block,
+//   twice the warps per SM for the same shared memory (the 4-warp kernel is MMA-latency bound at 8 warps per SM).
+//   MODE 1 / Q16 variant (<= 16 sequences per image: the pt loop has ONE): all four warps share the single 16-row query
 //   tile and split every 64-key block four ways (16 keys each), so the MMA work drops 4x and the kernel is purely
 //   HBM-bound on the K_c / V_c^T stream; each warp publishes its own (m, l, o) partial.
 //   Key blocks of 64 are staged with cp.async into a 2-stage ring (hi/lo planes of K and V, both [key][dim],
@@ -32,15 +34,18 @@ constexpr int MQ_STAGES = 2;
 constexpr int MQ_SMEM = MQ_STAGES * MQ_STAGE * 2 + MQ_STAGES * MQ_KB;  // tiles + per-stage key mask bytes
 constexpr int MQ_PART = 66;                   // floats per partial row: m, l, o[64]
 
-template <int NS, bool Q16>
-__global__ void __launch_bounds__(128, 3)
+template <int NS, int MODE>  // MODE 0: 4 warps = 4 row tiles; 1: 4 warps = 1 row tile x 4 key groups; 2: 8 warps = 4 x 2
+__global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 2 ? 2 : 3)
 cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, const float* __restrict__ q_f32, int Ncap,
                      const bf16* __restrict__ kc_hi, const bf16* __restrict__ kc_lo, const bf16* __restrict__ vc_hi,
                      const bf16* __restrict__ vc_lo, const uint8_t* __restrict__ kpm, int M, int nqb,
                      int npairs, int max_parts, float* __restrict__ partial, int* __restrict__ counters,
                      bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32) {
-  constexpr int NJ = Q16 ? 2 : 8;    // 8-key n-tiles of a block this warp scores
-  constexpr int NKK = Q16 ? 1 : 4;   // 16-key k-steps of a block this warp feeds into P.V
+  constexpr bool Q16 = MODE == 1;
+  constexpr int NT = MODE == 2 ? 256 : 128;           // threads
+  constexpr int NKG = MODE == 1 ? 4 : (MODE == 2 ? 2 : 1);  // key groups a 64-key block is split into
+  constexpr int NJ = 8 / NKG;        // 8-key n-tiles of a block this warp scores
+  constexpr int NKK = 4 / NKG;       // 16-key k-steps of a block this warp feeds into P.V
   extern __shared__ __align__(16) unsigned char mq_smem[];
   bf16* tiles = reinterpret_cast<bf16*>(mq_smem);
   uint8_t* smask = mq_smem + MQ_STAGES * MQ_STAGE * 2;
@@ -62,8 +67,9 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   const int gs = owner(static_cast<long>(pair) * nkb + nkb - 1) - first + 1;  // CTAs sharing this pair
   const int split = static_cast<int>(blockIdx.x) - first;
   const int q0 = qb * 64;
-  const int j0 = Q16 ? 2 * warp : 0, kk0 = Q16 ? warp : 0;
-  const int r_lo = (Q16 ? 0 : warp * 16) + g, r_hi = r_lo + 8;  // the two query rows (within the block) this lane holds
+  const int kg = Q16 ? warp : (warp >> 2);  // key group of this warp (MODE 0: always 0)
+  const int j0 = NJ * kg, kk0 = NKK * kg;
+  const int r_lo = (Q16 ? 0 : (warp & 3) * 16) + g, r_hi = r_lo + 8;  // the two query rows (within the block) this lane holds
   const bool live_lo = q0 + r_lo < Ncap, live_hi = q0 + r_hi < Ncap;
 
   const long kbase = (static_cast<long>(img) * 96 + h) * M * 64;  // K_c / V_c [img][dl(base)][h][key][64]
@@ -71,7 +77,7 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
     bf16* st = tiles + stage * MQ_STAGE;
     const int key0 = kb * MQ_KB;
 #pragma unroll
-    for (int i = tid; i < 512; i += 128) {
+    for (int i = tid; i < 512; i += NT) {
       // row r = key, 8 dims per 16-byte chunk; a warp instruction covers 4 consecutive keys = 512 contiguous bytes,
       // the whole block 8 KB contiguous per plane; keys >= M are zero-filled
       const int r = i >> 3, ch = (i & 7) * 8;
@@ -244,7 +250,7 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
 
-  if (!Q16 && gs == 1) {
+  if (MODE == 0 && gs == 1) {
     const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
     const long ob_lo = (static_cast<long>(img) * Ncap + q0 + r_lo) * 512 + h * 64 + 2 * t;
     const long ob_hi = (static_cast<long>(img) * Ncap + q0 + r_hi) * 512 + h * 64 + 2 * t;
@@ -267,11 +273,12 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   // ---- publish (m, l, o[64]) per query row and partial; the last CTA of the pair merges.  A partial is one key
   //      split (64 rows) or, for Q16, one warp of one key split (16 rows).
   constexpr int PR = Q16 ? 16 : 64;           // rows per partial
-  const int nparts = Q16 ? gs * 4 : gs;
+  const int nparts = gs * NKG;
+  const long pair_rows = static_cast<long>(max_parts) * NKG * PR;  // partial rows reserved per pair
   {
-    const int part = Q16 ? split * 4 + warp : split;
-    float* p_lo = partial + ((static_cast<long>(pair) * max_parts * 64) + part * PR + r_lo) * MQ_PART;
-    float* p_hi = partial + ((static_cast<long>(pair) * max_parts * 64) + part * PR + r_hi) * MQ_PART;
+    const int part = split * NKG + kg;
+    float* p_lo = partial + (static_cast<long>(pair) * pair_rows + part * PR + r_lo) * MQ_PART;
+    float* p_hi = partial + (static_cast<long>(pair) * pair_rows + part * PR + r_hi) * MQ_PART;
     if (t == 0) {
       p_lo[0] = m_lo; p_lo[1] = l_lo;
       p_hi[0] = m_hi; p_hi[1] = l_hi;
@@ -289,10 +296,11 @@ cross_attn_mq_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_l
   if (!last_flag) continue;
   __threadfence();
   {
-    constexpr int DPT = Q16 ? 8 : 32;         // dims per merging thread
-    const int row = Q16 ? tid >> 3 : tid >> 1, half = Q16 ? (tid & 7) * 8 : (tid & 1) * 32;
+    constexpr int DPT = 64 * PR / NT;         // dims per merging thread: 32 / 8 / 16
+    constexpr int TPR = 64 / DPT;             // threads per row
+    const int row = tid / TPR, half = (tid % TPR) * DPT;
     if (q0 + row < Ncap) {
-      const float* base = partial + (static_cast<long>(pair) * max_parts * 64 + row) * MQ_PART;
+      const float* base = partial + (static_cast<long>(pair) * pair_rows + row) * MQ_PART;
       const long sstride = static_cast<long>(PR) * MQ_PART;
       float mm = -INFINITY;
       for (int sidx = 0; sidx < nparts; ++sidx) mm = fmaxf(mm, base[sidx * sstride]);
@@ -353,7 +361,7 @@ void cross_attn_mq_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_p
 }
 
 size_t cross_attn_mq_partial_floats(int pairs, int max_parts) {
-  return static_cast<size_t>(pairs) * max_parts * 64 * MQ_PART;  // Q16: 4 warps x 16 rows per part -- same size
+  return static_cast<size_t>(pairs) * max_parts * 128 * MQ_PART;  // up to 2 key groups x 64 rows (or 4 x 16) per part
 }
 
 void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
@@ -368,8 +376,9 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
       ALM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, MQ_SMEM));
       pin_carveout(k);
     };
-    prep(cross_attn_mq_kernel<3, false>); prep(cross_attn_mq_kernel<1, false>);
-    prep(cross_attn_mq_kernel<3, true>); prep(cross_attn_mq_kernel<1, true>);
+    prep(cross_attn_mq_kernel<3, 0>); prep(cross_attn_mq_kernel<1, 0>);
+    prep(cross_attn_mq_kernel<3, 1>); prep(cross_attn_mq_kernel<1, 1>);
+    prep(cross_attn_mq_kernel<3, 2>); prep(cross_attn_mq_kernel<1, 2>);
     attr = true;
   }
   ALM_REQUIRE(q_f32 || q_hi, ALM_ERR_INVALID, "cross_attn_mq: no query operand");
@@ -377,12 +386,13 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
   ALM_REQUIRE(q16 || (out_hi && !out_f32), ALM_ERR_INVALID, "cross_attn_mq: fp32 output only on the <= 16-query path");
   const bool three = c->nsplit == 3 && (q_f32 || q_lo) && kc_lo && vc_lo;
   const int npairs = nimg * 8 * nqb;
-#define ALM_MQ_LAUNCH(NS, Q)                                                                                            \
-  cross_attn_mq_kernel<NS, Q><<<grid, 128, MQ_SMEM, c->stream>>>(q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vc_hi, vc_lo, kpm, \
-                                                                 M, nqb, npairs, max_parts, partial, counters,    \
-                                                                 out_hi, out_lo, out_f32)
-  if (three) { if (q16) ALM_MQ_LAUNCH(3, true); else ALM_MQ_LAUNCH(3, false); }
-  else       { if (q16) ALM_MQ_LAUNCH(1, true); else ALM_MQ_LAUNCH(1, false); }
+  const int mode = q16 ? 1 : (c->xattn_wg == 2 ? 2 : 0);
+#define ALM_MQ_LAUNCH(NS, MODE)                                                                                          \
+  cross_attn_mq_kernel<NS, MODE><<<grid, MODE == 2 ? 256 : 128, MQ_SMEM, c->stream>>>(                                   \
+      q_hi, q_lo, q_f32, Ncap, kc_hi, kc_lo, vc_hi, vc_lo, kpm, M, nqb, npairs, max_parts, partial, counters, out_hi,    \
+      out_lo, out_f32)
+  if (three) { if (mode == 1) ALM_MQ_LAUNCH(3, 1); else if (mode == 2) ALM_MQ_LAUNCH(3, 2); else ALM_MQ_LAUNCH(3, 0); }
+  else       { if (mode == 1) ALM_MQ_LAUNCH(1, 1); else if (mode == 2) ALM_MQ_LAUNCH(1, 2); else ALM_MQ_LAUNCH(1, 0); }
 #undef ALM_MQ_LAUNCH
   count_launch(c); check_launch("cross_attn_mq");
 }

@@ -84,7 +84,16 @@ ALM_API const char* alm_version(void);
  *          streams / in-flight batches can share the GPU),
  *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
  *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
- *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager). */
+ *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager),
+ *          "xattn_impl" (0 = fused flash-style decoder cross-attention [default]; 1 = unfused score GEMM + softmax +
+ *          P.V GEMM / fp32 single-query kernel, the A/B reference -- must be set before alm_omni_encode),
+ *          "xattn_ctas_per_sm" (persistent grid of the fused cross-attention: 1..3 CTAs per SM, default 2),
+ *          "sattn_wide" (1 = CTA per (sequence, head) self-attention step when few sequences are live [default]),
+ *          "enc_grid_cap" / "dec_grid_cap" (0 = off [default]; n = GEMM launches of alm_omni_encode / of the decode
+ *          loops use at most n CTAs), "decode_priority" (1 = decode loops run on internal high-priority streams;
+ *          default 0) -- co-scheduling knobs for several contexts on one GPU,
+ *          "debug_skip" (timing experiments only: bit mask of decoder-layer kernel classes NOT launched; results
+ *          are garbage; default 0). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
 /* kernels launched on this context since the last call with reset != 0 */
 ALM_API long alm_launch_count(alm_ctx* ctx, int reset);

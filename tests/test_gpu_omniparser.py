@@ -400,3 +400,29 @@ def test_fused_cross_attention_matches_gemm_path_and_oracle():
             m.ctx.set_option('sattn_wide', 1)
             m.ctx.set_option('xattn_ctas_per_sm', 2)
         assert _maxrel(lg[0][n], alt) < 2e-5, (n, _maxrel(lg[0][n], alt))
+
+
+def test_fused_cross_attention_8warp_variant_matches():
+    """`xattn_wg` 2 (8 warps: four 16-row tiles x two key groups per 64-key block) == the 4-warp kernel, on the same
+    ragged / masked / split case as above and on a batch of two images."""
+    m = model_for(0, 0.45)
+    v = m.vocab
+    g = torch.Generator().manual_seed(78)
+    img = torch.randn(2, 3, 240, 272, generator=g)
+    mask = torch.zeros(2, 240, 272, dtype=torch.bool)
+    mask[1, :, 224:] = True
+    img[mask[:, None].expand_as(img)] = 0
+    n_seq, L = 70, 5
+    seq = torch.cat([torch.randint(0, v.num_bins, (n_seq, 2), generator=g), torch.full((n_seq, 1), v.rec_sos_index),
+                     torch.randint(v.num_bins, v.recog_pad_index, (n_seq, L - 3), generator=g)], 1)
+    m.encode(img, mask)
+    for image in (0, 1):
+        for n in (70, 33):
+            ref = m.decode_logits(image, 'rec', seq[:n])
+            try:
+                m.ctx.set_option('xattn_wg', 2)
+                alt = m.decode_logits(image, 'rec', seq[:n])
+            finally:
+                m.ctx.set_option('xattn_wg', 1)
+            assert torch.isfinite(alt).all()
+            assert _maxrel(alt, ref) < 2e-5, (image, n, _maxrel(alt, ref))
