@@ -170,6 +170,7 @@ struct Ctx {
   bool skipped(int bit) const { return skip_scope && (debug_skip & bit); }
   cudaStream_t stream_hi = nullptr;  // internal high-priority stream for the decode loops
   cudaEvent_t ev_prio = nullptr;
+  cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync event: host waits that sleep instead of spinning
   int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
   int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial

@@ -147,6 +147,7 @@ void alm_free(alm_ctx* h) {
   if (h->c.stream2) cudaStreamDestroy(h->c.stream2);
   if (h->c.stream_hi) cudaStreamDestroy(h->c.stream_hi);
   if (h->c.ev_prio) cudaEventDestroy(h->c.ev_prio);
+  if (h->c.ev_block) cudaEventDestroy(h->c.ev_block);
   if (h->c.ev_fork) { cudaEventDestroy(h->c.ev_fork); cudaEventDestroy(h->c.ev_join); }
   for (auto e : h->c.ev_t) if (e) cudaEventDestroy(e);
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);

@@ -603,6 +603,17 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
   linear(c, u.h1, S, m->head[d][2], ACT_NONE, u.logits, nullptr);
 }
 
+// Sleep (do not spin) until everything enqueued on `s` has finished.  The decode loops wait for the GPU several
+// times per batch and a serving process keeps several contexts (host threads) per GPU in flight: spinning threads
+// would fight over the host cores (cgroup quotas are far below the visible CPU count on the GPU boxes).  The
+// device-to-pageable-host copies that follow each wait would otherwise spin inside cudaMemcpyAsync.
+void wait_stream(Ctx* c, cudaStream_t s) {
+  if (!c->ev_block)
+    ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+  ALM_CHECK_CUDA(cudaEventRecord(c->ev_block, s));
+  ALM_CHECK_CUDA(cudaEventSynchronize(c->ev_block));
+}
+
 struct HeadArgs {
   bool on = false;
   HeadCfg cfg{};
@@ -730,7 +741,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
     for (int b = 0; b < B; ++b)
       for (int i = 0; i < n_prompt; ++i) h[static_cast<size_t>(b) * Tpt + i] = static_cast<int>(pt_prompt[i]);
     ALM_CHECK_CUDA(cudaMemcpyAsync(pt_tok, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));  // h goes out of scope
+    wait_stream(c, c->stream);  // h goes out of scope (this also waits for the encoder)
   }
   fill_i32(c, finished, B, 0);
   fill_i32(c, ntok, B, 0);
@@ -750,6 +761,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
       run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, chunk, h);
       done += chunk;
       if (done < cfg.pt_seq_length) {  // every image hit EOS?  (one small sync per 16 tokens)
+        wait_stream(c, c->stream);
         ALM_CHECK_CUDA(cudaMemcpyAsync(fin.data(), finished, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
         if (std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; })) break;
@@ -757,6 +769,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
     }
   }
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[3], c->stream));
+  wait_stream(c, c->stream);
   std::vector<int> h_ntok(B), h_tok(static_cast<size_t>(B) * Tpt);
   std::vector<float> h_prob(static_cast<size_t>(B) * cfg.pt_seq_length);
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_ntok.data(), ntok, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -855,6 +868,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   ALM_CHECK_CUDA(cudaStreamWaitEvent(s0, c->ev_join, 0));
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[4], s0));
   c->timing_valid[1] = true;
+  wait_stream(c, c->stream);
   for (int phase = 1; phase <= 2; ++phase) {
     const int len = phase == 1 ? cfg.poly_length : cfg.rec_length;
     const int T = 3 + len;
