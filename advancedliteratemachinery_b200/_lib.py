@@ -70,6 +70,17 @@ SIGNATURES = {
                                    C.c_int]),
     'alm_op_window_attention': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int]),
+    # host-only post-processing (no context, no GPU)
+    'alm_post_last_error': (C.c_char_p, []),
+    'alm_post_omni_spotting': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_char_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_size_t]),
+    'alm_post_omni_json': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_char_p, C.c_long, C.c_long, C.c_char_p, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t)]),
+    'alm_post_mgp_fuse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                    C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p, C.c_void_p]),
 }
 
 

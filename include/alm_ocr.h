@@ -200,6 +200,45 @@ ALM_API int alm_op_layernorm(alm_ctx* ctx, const float* x, const float* gamma, c
 ALM_API int alm_op_window_attention(alm_ctx* ctx, const float* qkv, const float* bias_table /*[169,heads]*/, float* out,
                             int B, int nWh, int nWw, int C, int heads, int shift);
 
+/* ---- post-processing (host only: no context, no GPU) ------------------------ */
+/* Sequences -> structured result, the step right after the forward.  Errors: negative ALM_ERR_*; the message of
+ * the last failing call of the calling thread is returned by alm_post_last_error(). */
+ALM_API const char* alm_post_last_error(void);
+
+/* Replaces decode_pred_seq + decode_seq (OCR/OmniParser/engine/val.py:70-100, utils/misc.py:147-189) for ONE image:
+ *   pt [2*n] / poly [32*n] / rec [n*rec_length] int64 ids and rec_prob [n*rec_length] f32 as returned by
+ *   alm_omni_decode (one row of its outputs); chars = args.chars as UTF-8 (one code point per class id
+ *   num_bins + i); orig_h / orig_w = target['orig_size'].
+ * Outputs (caller buffers): pts [n,2] and polys [n,32] doubles holding the reference's float32 values
+ * (id / num_bins * size, both steps rounded to f32 like the torch expressions), scores [n] doubles
+ * (sum(p) / (len + 1e-5) in double), texts: n NUL-terminated UTF-8 strings at stride text_stride bytes. */
+ALM_API int alm_post_omni_spotting(const int64_t* pt, const int64_t* poly, const int64_t* rec, const float* rec_prob, int n,
+                                   int rec_length, int num_bins, int recog_pad_index, int rec_eos_index, const char* chars,
+                                   long orig_h, long orig_w, double* pts, double* polys, double* scores, char* texts,
+                                   size_t text_stride);
+/* The same results as the JSON text `json.dumps(results, indent=4)` writes for this image (val.py:63-67; keys
+ * image_id, pts, score, polys, rec; Python float repr; ensure_ascii escapes).  Writes at most cap bytes incl. NUL
+ * and always stores the needed size (incl. NUL) in *needed; returns ALM_ERR_INVALID if cap is too small. */
+ALM_API int alm_post_omni_json(const int64_t* pt, const int64_t* poly, const int64_t* rec, const float* rec_prob, int n,
+                               int rec_length, int num_bins, int recog_pad_index, int rec_eos_index, const char* chars,
+                               long orig_h, long orig_w, const char* image_id, char* json, size_t cap, size_t* needed);
+
+/* MGP-STR A^3 fusion (OCR/MGP-STR/test_final.py:176-240, demo.py:36-112, utils.py:52-87) for B crops.
+ *   ids / prob: [3][B,T] int32 top-1 ids and f32 max-softmax probabilities of the char, bpe and wp heads INCLUDING
+ *   position 0 (exactly what alm_mgpstr_forward returns; T = 27).
+ *   tables: token strings per id, UTF-8 -- char: ['[GO]', '[s]'] + opt.character; bpe: the byte-decoded GPT-2 token
+ *   strings; wp: the WordPiece tokens of bert-base-uncased.  (The reference obtains them from the HuggingFace
+ *   tokenizers; they are data, passed in by the caller.)
+ * Per crop and head: text (pruned at the end-of-sentence marker the way the reference prunes it -- string find of
+ * '[s]' / '#' / '[SEP]', including its -1 quirk) and confidence = cumprod of the max-probs up to the EOS position
+ * (first id 1 / 2 / 102 for char / bpe / wp; char uses the STRING index like the reference); fused = the head with
+ * the largest confidence (strictly greater, in char, bpe, wp order; none if all are 0).
+ * Outputs: texts [3][B] and fused [B] strings at stride text_stride; conf [3][B] f32; source [B] int32 (0 char, 1 bpe,
+ * 2 wp, -1 none). */
+ALM_API int alm_post_mgp_fuse(const int32_t* ids, const float* prob, int B, int T, const char* const* char_table, int n_char,
+                              const char* const* bpe_table, int n_bpe, const char* const* wp_table, int n_wp, char* texts,
+                              char* fused, size_t text_stride, float* conf, int32_t* source);
+
 #ifdef __cplusplus
 }
 #endif
