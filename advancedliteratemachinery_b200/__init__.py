@@ -11,4 +11,4 @@ from ._lib import AlmError, Context, LIB_PATH  # noqa: F401
 from .nested_tensor import NestedTensor, nested_tensor_from_tensor_list  # noqa: F401
 from .omniparser import OmniParserB200, OmniVocab  # noqa: F401
 from .mgp_str import MGPSTRB200  # noqa: F401
-from . import postprocess  # noqa: F401
+from . import postprocess, preprocess  # noqa: F401

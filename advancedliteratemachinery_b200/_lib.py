@@ -44,6 +44,7 @@ SIGNATURES = {
     'alm_version': (C.c_char_p, []),
     'alm_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     'alm_launch_count': (C.c_long, [C.c_void_p, C.c_int]),
+    'alm_synchronize': (C.c_int, [C.c_void_p]),
     'alm_profile_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     'alm_trace_read': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     'alm_bench_graph_floor': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -70,6 +71,13 @@ SIGNATURES = {
                                    C.c_int]),
     'alm_op_window_attention': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int]),
+    # test-time image pipeline
+    'alm_pre_omni_plan': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]),
+    'alm_pre_coeffs': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_size_t]),
+    'alm_pre_omni_pages': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    'alm_pre_mgp_crops': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     # host-only post-processing (no context, no GPU)
     'alm_post_last_error': (C.c_char_p, []),
     'alm_post_omni_spotting': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -116,6 +124,9 @@ class Context:
     def check(self, rc):
         if rc != ALM_OK:
             raise AlmError(rc, self.lib.alm_last_error(self.h).decode())
+
+    def synchronize(self):
+        self.check(self.lib.alm_synchronize(self.h))
 
     def set_option(self, key: str, value: int):
         self.check(self.lib.alm_set_option(self.h, key.encode(), int(value)))

@@ -6,6 +6,7 @@
 #include "alm_internal.h"
 #include "mgp.h"
 #include "omni.h"
+#include "pre.h"
 
 using namespace alm;
 
@@ -403,6 +404,93 @@ int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors,
     else if (model_kind == ALM_MODEL_MGPSTR) mgp_load(&h->c, t);
     else throw AlmError{ALM_ERR_INVALID, "unknown model kind"};
     ALM_CHECK_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+int alm_synchronize(alm_ctx* h) {
+  return guarded(h, [&] { ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream)); });
+}
+
+// ------------------------------------------------------------------------------------------ pre-processing
+namespace {
+
+// device copies of the caller's uint8 HWC images (host pointers are staged into the workspace on the stream)
+std::vector<PreImage> stage_images(alm_ctx* h, const uint8_t* const* rgb, const int* heights, const int* widths, int n) {
+  Ctx* c = &h->c;
+  c->ensure_ws();
+  std::vector<PreImage> imgs(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) {
+    ALM_REQUIRE(rgb[i] && heights[i] > 0 && widths[i] > 0, ALM_ERR_INVALID, "image pointer / size");
+    const size_t bytes = static_cast<size_t>(heights[i]) * widths[i] * 3;
+    const uint8_t* d = rgb[i];
+    if (!is_device_ptr(d)) {
+      uint8_t* slot = c->ws.get<uint8_t>(bytes);
+      ALM_CHECK_CUDA(cudaMemcpyAsync(slot, rgb[i], bytes, cudaMemcpyHostToDevice, c->stream));
+      d = slot;
+    }
+    imgs[static_cast<size_t>(i)] = PreImage{d, heights[i], widths[i], 0, 0};
+  }
+  return imgs;
+}
+
+}  // namespace
+
+int alm_pre_omni_plan(const int* heights, const int* widths, int n, int test_min_size, int test_max_size, int* sizes,
+                      int* Hmax, int* Wmax) {
+  if (!heights || !widths || n < 0 || test_min_size <= 0 || !sizes || !Hmax || !Wmax) return ALM_ERR_INVALID;
+  int hm = 0, wm = 0;
+  for (int i = 0; i < n; ++i) {
+    if (heights[i] <= 0 || widths[i] <= 0) return ALM_ERR_INVALID;
+    pre_omni_size(heights[i], widths[i], test_min_size, test_max_size, &sizes[2 * i], &sizes[2 * i + 1]);
+    hm = std::max(hm, sizes[2 * i]);
+    wm = std::max(wm, sizes[2 * i + 1]);
+  }
+  *Hmax = hm; *Wmax = wm;
+  return ALM_OK;
+}
+
+int alm_pre_coeffs(int in_size, int out_size, int filter, int* ksize, int* bounds, int* coefs, size_t cap_ints) {
+  try {
+    return pre_coeffs(in_size, out_size, filter, ksize, bounds, coefs, cap_ints);
+  } catch (...) {
+    return ALM_ERR_INVALID;
+  }
+}
+
+int alm_pre_omni_pages(alm_ctx* h, const uint8_t* const* rgb, const int* heights, const int* widths, int n,
+                       int test_min_size, int test_max_size, float* tensors, uint8_t* mask) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(rgb && heights && widths && n > 0 && test_min_size > 0 && tensors && mask, ALM_ERR_INVALID,
+                "alm_pre_omni_pages arguments");
+    ALM_REQUIRE(is_device_ptr(tensors) && is_device_ptr(mask), ALM_ERR_INVALID, "outputs must be device buffers");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    std::vector<PreImage> imgs = stage_images(h, rgb, heights, widths, n);
+    int Hc = 0, Wc = 0;
+    for (auto& im : imgs) {
+      pre_omni_size(im.h, im.w, test_min_size, test_max_size, &im.oh, &im.ow);
+      Hc = std::max(Hc, im.oh);
+      Wc = std::max(Wc, im.ow);
+    }
+    pre_resize_batch(c, imgs, PRE_BILINEAR, true, tensors, Hc, Wc, mask);
+    c->ws.release(mk);
+  });
+}
+
+int alm_pre_mgp_crops(alm_ctx* h, const uint8_t* const* rgb, const int* heights, const int* widths, int n, int imgH,
+                      int imgW, float* out) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(rgb && heights && widths && n > 0 && imgH > 0 && imgW > 0 && out, ALM_ERR_INVALID,
+                "alm_pre_mgp_crops arguments");
+    ALM_REQUIRE(is_device_ptr(out), ALM_ERR_INVALID, "output must be a device buffer");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    const size_t mk = c->ws.mark();
+    std::vector<PreImage> imgs = stage_images(h, rgb, heights, widths, n);
+    for (auto& im : imgs) { im.oh = imgH; im.ow = imgW; }
+    pre_resize_batch(c, imgs, PRE_BICUBIC, false, out, imgH, imgW, nullptr);
+    c->ws.release(mk);
   });
 }
 

@@ -95,6 +95,8 @@ ALM_API const char* alm_version(void);
  *          "debug_skip" (timing experiments only: bit mask of decoder-layer kernel classes NOT launched; results
  *          are garbage; default 0). */
 ALM_API int alm_set_option(alm_ctx* ctx, const char* key, long value);
+/* block until everything enqueued on the context's stream has finished */
+ALM_API int alm_synchronize(alm_ctx* ctx);
 /* kernels launched on this context since the last call with reset != 0 */
 ALM_API long alm_launch_count(alm_ctx* ctx, int reset);
 
@@ -199,6 +201,29 @@ ALM_API int alm_op_layernorm(alm_ctx* ctx, const float* x, const float* gamma, c
 /* Swin W-MSA core on an already windowed qkv tensor [B*nWh*nWw*49, 3C] (swin_transformer.py:127-148). */
 ALM_API int alm_op_window_attention(alm_ctx* ctx, const float* qkv, const float* bias_table /*[169,heads]*/, float* out,
                             int B, int nWh, int nWw, int C, int heads, int shift);
+
+/* ---- test-time image pipeline on the GPU ----------------------------------- */
+/* Replaces RandomResize([test_min_size], test_max_size) -> ToTensor -> Normalize -> nested_tensor_from_tensor_list
+ * (OCR/OmniParser/dataset/__init__.py:109-113, dataset/transforms.py:249-298,312-322, utils/nested_tensor.py:37-54)
+ * for a batch of decoded 8-bit RGB pages.  The resize is Pillow's two-pass 8-bit bilinear resampling, reproduced bit
+ * for bit (integer kernels; weights computed like Pillow computes them); ToTensor / Normalize are the same float32
+ * operations, so tensors and mask equal the reference's.
+ * alm_pre_omni_plan (host only): resized (h, w) per page = get_size_with_aspect_ratio, and the batch canvas.
+ * alm_pre_omni_pages: rgb[i] = host or device pointer to page i, [heights[i]][widths[i]][3] uint8.  Outputs are
+ * DEVICE buffers sized from the plan: tensors f32 [n,3,Hmax,Wmax] (zero padded), mask u8 [n,Hmax,Wmax] (1 = pad);
+ * they feed alm_omni_encode directly. */
+ALM_API int alm_pre_omni_plan(const int* heights, const int* widths, int n, int test_min_size, int test_max_size,
+                              int* sizes /*[n][2] resized h, w*/, int* Hmax, int* Wmax);
+/* Introspection (host only): the 22-bit fixed-point weights of ONE resampling pass exactly as the kernels use them
+ * (filter 0 = bilinear, 1 = bicubic): bounds [out_size][2] = (first source index, taps), coefs [out_size][*ksize].
+ * Call with coefs == NULL to obtain *ksize first (returns ALM_ERR_INVALID after storing it). */
+ALM_API int alm_pre_coeffs(int in_size, int out_size, int filter, int* ksize, int* bounds, int* coefs, size_t cap_ints);
+ALM_API int alm_pre_omni_pages(alm_ctx* ctx, const uint8_t* const* rgb, const int* heights, const int* widths, int n,
+                               int test_min_size, int test_max_size, float* tensors, uint8_t* mask);
+/* Replaces `img.resize((imgW, imgH), Image.BICUBIC)` + ToTensor (OCR/MGP-STR/demo.py:126-132, dataset.py:459-461):
+ * out = DEVICE f32 [n,3,imgH,imgW] in [0,1], the input of alm_mgpstr_forward. */
+ALM_API int alm_pre_mgp_crops(alm_ctx* ctx, const uint8_t* const* rgb, const int* heights, const int* widths, int n,
+                              int imgH, int imgW, float* out);
 
 /* ---- post-processing (host only: no context, no GPU) ------------------------ */
 /* Sequences -> structured result, the step right after the forward.  Errors: negative ALM_ERR_*; the message of
