@@ -20,11 +20,12 @@
 
 #include "alm_internal.h"
 #include "pre.h"
+#include "preproc_core.h"
 
 namespace alm {
 namespace {
 
-constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow: PRECISION_BITS
+constexpr int kPrecisionBits = pre_core::kPrecisionBits;  // Pillow: PRECISION_BITS
 
 double filt_bilinear(double x) {
   if (x < 0.0) x = -x;
@@ -81,67 +82,25 @@ Coefs precompute(int in_size, int out_size, int filter) {
   return c;
 }
 
-__device__ __forceinline__ int clip8(int v) {
-  v >>= kPrecisionBits;
-  return v < 0 ? 0 : (v > 255 ? 255 : v);
-}
-
-// horizontal pass: src [h][w][3] u8 -> dst [h][ow][3] u8; one thread per output pixel
+// horizontal pass: src [h][w][3] u8 -> dst [h][ow][3] u8; one thread per output pixel (body in preproc_core.h)
 __global__ void resample_h_kernel(const uint8_t* __restrict__ src, int h, int w, int ow, const int* __restrict__ bounds,
                                   const int* __restrict__ coefs, int ksize, uint8_t* __restrict__ dst) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long>(h) * ow) return;
-  const int y = static_cast<int>(i / ow), xx = static_cast<int>(i - static_cast<long>(y) * ow);
-  const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
-  const int* k = coefs + static_cast<long>(xx) * ksize;
-  int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-  const uint8_t* p = src + (static_cast<long>(y) * w + xmin) * 3;
-  for (int x = 0; x < n; ++x) {
-    const int kk = k[x];
-    s0 += p[3 * x] * kk; s1 += p[3 * x + 1] * kk; s2 += p[3 * x + 2] * kk;
-  }
-  uint8_t* o = dst + i * 3;
-  o[0] = static_cast<uint8_t>(clip8(s0)); o[1] = static_cast<uint8_t>(clip8(s1)); o[2] = static_cast<uint8_t>(clip8(s2));
+  if (i < static_cast<long>(h) * ow) pre_core::resample_h_px(i, src, w, ow, bounds, coefs, ksize, dst);
 }
 
 // vertical pass fused with ToTensor (/255) and Normalize ((x - mean) / std), writing the planar float canvas:
 // src [h][ow][3] u8 -> dst[c][yy][xx] (row stride Wc, plane stride Hc*Wc); one thread per output pixel
-__global__ void resample_v_norm_kernel(const uint8_t* __restrict__ src, int h, int ow, int oh, const int* __restrict__ bounds,
+__global__ void resample_v_norm_kernel(const uint8_t* __restrict__ src, int ow, int oh, const int* __restrict__ bounds,
                                        const int* __restrict__ coefs, int ksize, float* __restrict__ dst, long plane, int Wc,
-                                       float m0, float m1, float m2, float d0, float d1, float d2, int normalize) {
+                                       pre_core::Norm nm) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long>(oh) * ow) return;
-  const int yy = static_cast<int>(i / ow), xx = static_cast<int>(i - static_cast<long>(yy) * ow);
-  const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
-  const int* k = coefs + static_cast<long>(yy) * ksize;
-  int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-  const uint8_t* p = src + (static_cast<long>(ymin) * ow + xx) * 3;
-  for (int y = 0; y < n; ++y) {
-    const int kk = k[y];
-    const uint8_t* q = p + static_cast<long>(y) * ow * 3;
-    s0 += q[0] * kk; s1 += q[1] * kk; s2 += q[2] * kk;
-  }
-  // F.to_tensor: uint8 -> float32, .div(255); F.normalize: .sub_(mean).div_(std) -- IEEE float32, no contraction
-  float f0 = __fdiv_rn(static_cast<float>(clip8(s0)), 255.0f);
-  float f1 = __fdiv_rn(static_cast<float>(clip8(s1)), 255.0f);
-  float f2 = __fdiv_rn(static_cast<float>(clip8(s2)), 255.0f);
-  if (normalize) {
-    f0 = __fdiv_rn(__fsub_rn(f0, m0), d0);
-    f1 = __fdiv_rn(__fsub_rn(f1, m1), d1);
-    f2 = __fdiv_rn(__fsub_rn(f2, m2), d2);
-  }
-  const long o = static_cast<long>(yy) * Wc + xx;
-  dst[o] = f0; dst[plane + o] = f1; dst[2 * plane + o] = f2;
+  if (i < static_cast<long>(oh) * ow) pre_core::resample_v_norm_px(i, src, ow, bounds, coefs, ksize, dst, plane, Wc, nm);
 }
 
 __global__ void pad_mask_kernel(uint8_t* __restrict__ mask, int n, int Hc, int Wc, const int* __restrict__ sizes) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long per = static_cast<long>(Hc) * Wc;
-  if (i >= n * per) return;
-  const int b = static_cast<int>(i / per);
-  const long r = i - b * per;
-  const int y = static_cast<int>(r / Wc), x = static_cast<int>(r - static_cast<long>(y) * Wc);
-  mask[i] = (y >= sizes[2 * b] || x >= sizes[2 * b + 1]) ? 1 : 0;  // True = padding (nested_tensor.py:47-51)
+  if (i < static_cast<long>(n) * Hc * Wc) pre_core::pad_mask_px(i, mask, Hc, Wc, sizes);
 }
 
 }  // namespace
@@ -222,9 +181,10 @@ void pre_resize_batch(Ctx* c, const std::vector<PreImage>& imgs, int filter, boo
     resample_h_kernel<<<static_cast<unsigned>((nh + 255) / 256), 256, 0, c->stream>>>(
         im.dev_rgb, im.h, im.w, im.ow, dev + wh.first, dev + wh.first + 2 * static_cast<size_t>(im.ow), wh.second, tmp);
     count_launch(c); check_launch("resample_h");
+    const pre_core::Norm nm{{mean[0], mean[1], mean[2]}, {sd[0], sd[1], sd[2]}, normalize ? 1 : 0};
     resample_v_norm_kernel<<<static_cast<unsigned>((nv + 255) / 256), 256, 0, c->stream>>>(
-        tmp, im.h, im.ow, im.oh, dev + wv.first, dev + wv.first + 2 * static_cast<size_t>(im.oh), wv.second,
-        out + static_cast<long>(b) * 3 * plane, plane, Wc, mean[0], mean[1], mean[2], sd[0], sd[1], sd[2], normalize ? 1 : 0);
+        tmp, im.ow, im.oh, dev + wv.first, dev + wv.first + 2 * static_cast<size_t>(im.oh), wv.second,
+        out + static_cast<long>(b) * 3 * plane, plane, Wc, nm);
     count_launch(c); check_launch("resample_v_norm");
   }
   if (mask) {

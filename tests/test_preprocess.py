@@ -61,6 +61,63 @@ def test_kernel_weights_equal_the_pinned_oracle():
             assert np.array_equal(bounds, ob) and np.array_equal(coefs, ok), (in_size, out_size, name)
 
 
+def _emu():
+    """Build tests/emu/preproc_emu.cpp (host compile of the kernels' per-pixel bodies) and bind it."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(tempfile.mkdtemp(), 'preproc_emu.so')
+    subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-std=c++17',
+                           os.path.join(here, 'emu', 'preproc_emu.cpp'), '-o', so])
+    return C.CDLL(so)
+
+
+def _emu_batch(lib, images, sizes, canvas, filter_name, normalize):
+    """The launch sequence of pre_resize_batch (preproc.cu) on the host emulation."""
+    from advancedliteratemachinery_b200 import preprocess as P
+    Hc, Wc = canvas
+    n = len(images)
+    out = np.zeros((n, 3, Hc, Wc), dtype=np.float32)              # cudaMemsetAsync(out, 0)
+    mean = np.asarray([0.485, 0.456, 0.406], dtype=np.float32)
+    sd = np.asarray([0.229, 0.224, 0.225], dtype=np.float32)
+    for b, (im, (oh, ow)) in enumerate(zip(images, sizes)):
+        im = np.ascontiguousarray(im)
+        hb, hk = P.resample_coeffs(im.shape[1], ow, filter_name)
+        vb, vk = P.resample_coeffs(im.shape[0], oh, filter_name)
+        lib.emu_resize_norm(im.ctypes.data, im.shape[0], im.shape[1], oh, ow, hb.ctypes.data, hk.ctypes.data, hk.shape[1],
+                            vb.ctypes.data, vk.ctypes.data, vk.shape[1], out[b].ctypes.data, Hc * Wc, Wc, mean.ctypes.data,
+                            sd.ctypes.data, 1 if normalize else 0)
+    mask = np.zeros((n, Hc, Wc), dtype=np.uint8)
+    sz = np.asarray(sizes, dtype=np.int32)
+    lib.emu_pad_mask(mask.ctypes.data, n, Hc, Wc, sz.ctypes.data)
+    return out, mask
+
+
+def test_kernel_bodies_on_the_host_equal_reference_fixtures():
+    """The per-pixel functions the CUDA kernels execute (csrc/preproc_core.h), compiled for the host and driven in the
+    kernels' launch order with the library's own size plan and weights, reproduce the reference outputs bit for bit."""
+    import ctypes as C
+    from advancedliteratemachinery_b200 import preprocess as P
+    lib = _emu()
+    for f in (lib.emu_resize_norm, lib.emu_pad_mask):
+        f.restype = None
+    lib.emu_resize_norm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.emu_pad_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    z, pages = _omni()
+    sizes, canvas = P.omni_plan([p.shape[:2] for p in pages], int(z['min_size']), int(z['max_size']))
+    out, mask = _emu_batch(lib, pages, sizes, canvas, 'bilinear', True)
+    assert np.array_equal(out.view(np.uint32), z['tensors'].view(np.uint32))     # bit pattern, not just value
+    assert np.array_equal(mask.astype(bool), z['mask'])
+    zc, crops = _mgp()
+    out, _ = _emu_batch(lib, crops, [(32, 128)] * len(crops), (32, 128), 'bicubic', False)
+    assert np.array_equal(out.view(np.uint32), zc['out'].view(np.uint32))
+
+
 def test_size_plan_equals_reference_rule():
     """alm_pre_omni_plan (host-only C entry point) == RandomResize.get_size_with_aspect_ratio on 400 recorded cases."""
     from advancedliteratemachinery_b200 import preprocess as P
