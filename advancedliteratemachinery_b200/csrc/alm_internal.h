@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <tuple>
 #include <unordered_map>
 #include <string>
 #include <vector>
@@ -156,6 +157,7 @@ struct Ctx {
     }
   };
   std::unordered_map<TmapKey, CUtensorMap, TmapHash> tmap_cache;
+  std::map<std::tuple<const void*, int, long>, CUtensorMap> xattn_tmaps;  // K/V cache planes (xattn_tma.cu)
   // Co-scheduling of in-flight batches: every tcgen05 GEMM CTA needs a whole SM (231 KB of shared memory) for the
   // whole launch, so a full-width encoder GEMM shuts every other stream out.  enc_grid_cap / dec_grid_cap bound the
   // persistent GEMM grids of the encoder / the decode loops; decode_priority runs the decode loops on internal
@@ -182,7 +184,8 @@ struct Ctx {
   int sattn_wide = 1;  // CTA-per-(sequence, head) self-attention step when there are few sequences
   int xattn_wg = 1;  // 2 = 8-warp variant of the 64-query fused cross-attention (two key groups per block)
   int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
-  int xattn_impl = 0;  // 0 = fused flash-style multi-query cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM
+  int xattn_impl = 0;  // 0 = fused flash-style cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM,
+                       // 2 = fused, TMA + mbarrier pipeline (xattn_tma.cu; experimental)
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;

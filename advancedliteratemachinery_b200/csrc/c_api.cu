@@ -181,7 +181,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
         ALM_CHECK_CUDA(cudaMemset(h->c.detail_buf, 0, 64 * 6 * sizeof(unsigned long long)));
       }
     } else if (k == "xattn_impl") {
-      h->c.xattn_impl = value ? 1 : 0;
+      ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "xattn_impl must be 0, 1 or 2");
+      h->c.xattn_impl = static_cast<int>(value);
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
     } else if (k == "enc_grid_cap") {

@@ -421,6 +421,7 @@ struct DecodeBufs {
   int xq_splits = 1;
   int mq_grid = 1, mq_parts = 1;  // fused cross-attention: persistent grid size, partial slots per (image, head, query block)
   bool fused_xattn = false;
+  bool tma_xattn = false;  // fused, experimental TMA + mbarrier variant (xattn_impl 2)
   SplitBuf prob;
   float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
   float* vc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -451,10 +452,12 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     d.h1f = c->ws.get<float>(S * 512);
     d.qkv = c->ws.get<float>(S * 1536);
   }
-  if (c->xattn_impl == 0) {
+  if (c->xattn_impl == 0 || c->xattn_impl == 2) {
     int pairs = 0;
     d.fused_xattn = true;
-    cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
+    d.tma_xattn = c->xattn_impl == 2;
+    if (d.tma_xattn) cross_attn_tma_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
+    else cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
     d.xq_partial = c->ws.get<float>(cross_attn_mq_partial_floats(pairs, d.mq_parts));
     d.xq_counters = c->ws.get<int>(pairs);
     fill_i32(c, d.xq_counters, pairs, 0);
@@ -473,6 +476,22 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     d.vc[l] = c->ws.get<float>(S * Tmax * 512);
   }
   return d;
+}
+
+// Fused cross-attention of `nimg` images x Ncap queries against decoder-layer dl of the cached K_c / V_c
+void fused_xattn(Ctx* c, OmniModel* m, DecodeBufs& u, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int img0, int nimg,
+                 int Ncap, long dl, bf16* out_hi, bf16* out_lo, float* out_f32) {
+  const int M = m->M;
+  const uint8_t* kpm = m->kpm + static_cast<long>(img0) * M;
+  if (u.tma_xattn) {
+    cross_attn_tma(c, q_hi, q_lo, q_f32, nimg, Ncap, m->kc_hi, m->kc_lo, m->vc_hi, m->vc_lo, static_cast<long>(m->B) * 96,
+                   static_cast<int>(img0 * 96 + dl * 8), kpm, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters, out_hi,
+                   out_lo, out_f32);
+    return;
+  }
+  const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
+  cross_attn_mq(c, q_hi, q_lo, q_f32, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff, m->vc_lo + koff, kpm, M,
+                u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters, out_hi, out_lo, out_f32);
 }
 
 // One decoder pass over the token at position *u.tpos of every sequence (pre-norm layer, transformer.py:430-454,
@@ -505,9 +524,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
-        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff, m->vc_lo + koff,
-                      m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
-                      nullptr, nullptr, u.of);
+        fused_xattn(c, m, u, nullptr, nullptr, u.qf, img0, nimg, 1, dl, nullptr, nullptr, u.of);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
                       m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, nullptr,
@@ -547,9 +564,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
       const long voff = (static_cast<long>(img0) * 6144 + dl * 512) * Mpad;
       if (u.fused_xattn)
-        cross_attn_mq(c, nullptr, nullptr, u.qf, nimg, 1, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff, m->vc_lo + koff,
-                      m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters,
-                      u.o.hi, u.o.lo, nullptr);
+        fused_xattn(c, m, u, nullptr, nullptr, u.qf, img0, nimg, 1, dl, u.o.hi, u.o.lo, nullptr);
       else
         cross_attn_q1(c, u.qf, m->kc_hi + koff, m->kc_lo + koff, m->vt_hi + voff, m->vt_lo + voff,
                       m->kpm + static_cast<long>(img0) * M, nimg, M, Mpad, u.xq_partial, u.xq_counters, u.xq_splits, u.o.hi,
@@ -557,10 +572,7 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
     } else if (u.fused_xattn) {
       // Ncap queries per image: scores, mask, online softmax and P.V fused; K_c / V_c^T streamed once per layer-step
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
-      const long koff = (static_cast<long>(img0) * 96 + dl * 8) * M * 64;
-      cross_attn_mq(c, u.q.hi, u.q.lo, nullptr, nimg, Ncap, m->kc_hi + koff, m->kc_lo + koff, m->vc_hi + koff,
-                    m->vc_lo + koff, m->kpm + static_cast<long>(img0) * M, M, u.mq_grid, u.mq_parts, u.xq_partial,
-                    u.xq_counters, u.o.hi, u.o.lo, nullptr);
+      fused_xattn(c, m, u, u.q.hi, u.q.lo, nullptr, img0, nimg, Ncap, dl, u.o.hi, u.o.lo, nullptr);
     } else {
       linear(c, u.lnp, S, w.ca_q, ACT_NONE, nullptr, &u.q);
       {

@@ -86,7 +86,8 @@ ALM_API const char* alm_version(void);
  *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager),
  *          "xattn_impl" (0 = fused flash-style decoder cross-attention [default]; 1 = unfused score GEMM + softmax +
- *          P.V GEMM / fp32 single-query kernel, the A/B reference -- must be set before alm_omni_encode),
+ *          P.V GEMM / fp32 single-query kernel, the A/B reference -- must be set before alm_omni_encode; 2 = fused with a
+ *          TMA + mbarrier operand pipeline, experimental),
  *          "xattn_ctas_per_sm" (persistent grid of the fused cross-attention: 1..3 CTAs per SM, default 2),
  *          "sattn_wide" (1 = CTA per (sequence, head) self-attention step when few sequences are live [default]),
  *          "enc_grid_cap" / "dec_grid_cap" (0 = off [default]; n = GEMM launches of alm_omni_encode / of the decode

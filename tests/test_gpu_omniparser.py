@@ -449,3 +449,42 @@ def test_more_than_32_pages_leave_the_skinny_path_and_stay_batch_invariant():
             if a is not None:
                 for x, y in zip(a[0], b[0]):
                     assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(os.environ.get('ALM_RUN_UNVALIDATED') != '1',
+                    reason='xattn_impl 2 (TMA + mbarrier pipeline) was written after the round-1 GPU budget was spent')
+def test_tma_cross_attention_variant_matches_the_default_kernel():
+    """`xattn_impl` 2 (csrc/xattn_tma.cu) against the default fused kernel: 70 / 33 sequences (8 math warps), 10 and 1
+    (the 16-row pt variant), ragged key range, masked keys, two images, then a whole greedy decode."""
+    from advancedliteratemachinery_b200 import NestedTensor
+    m = model_for(0, 0.45)
+    v = m.vocab
+    g = torch.Generator().manual_seed(79)
+    img = torch.randn(2, 3, 240, 272, generator=g)
+    mask = torch.zeros(2, 240, 272, dtype=torch.bool)
+    mask[1, :, 224:] = True
+    img[mask[:, None].expand_as(img)] = 0
+    seq = torch.cat([torch.randint(0, v.num_bins, (70, 2), generator=g), torch.full((70, 1), v.rec_sos_index),
+                     torch.randint(v.num_bins, v.recog_pad_index, (70, 2), generator=g)], 1)
+    m.encode(img, mask)
+    try:
+        for image in (0, 1):
+            for n in (70, 33, 10, 1):
+                m.ctx.set_option('xattn_impl', 0)
+                ref = m.decode_logits(image, 'rec', seq[:n])
+                m.ctx.set_option('xattn_impl', 2)
+                alt = m.decode_logits(image, 'rec', seq[:n])
+                assert torch.isfinite(alt).all()
+                assert _maxrel(alt, ref) < 2e-5, (image, n, _maxrel(alt, ref))
+        m.vocab.pt_seq_length = 6
+        m.ctx.set_option('xattn_impl', 0)
+        a = m.forward_batch(NestedTensor(img.cuda(), mask.cuda()))
+        m.ctx.set_option('xattn_impl', 2)
+        b = m.forward_batch(NestedTensor(img.cuda(), mask.cuda()))
+        for x, y in zip(a, b):
+            assert (x is None) == (y is None)
+            if x is not None:
+                for p, q in zip(x[0], y[0]):
+                    assert torch.equal(p, q)
+    finally:
+        m.ctx.set_option('xattn_impl', 0)
