@@ -7,7 +7,7 @@
 #        STEPS=8 bash tools/gpu_sweep.sh 4: 4:xattn_impl=2
 mkdir -p gpurun_out
 ALM_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_preprocess.py tests/test_gpu_omniparser.py -m gpu -q \
-    -k "preprocess or gpu_omni_pages or gpu_mgp_crops or page_scale or more_than_32 or tma_cross_attention" > gpurun_out/pytest_unvalidated.log 2>&1
+    -k "preprocess or gpu_omni_pages or gpu_mgp_crops or page_scale or more_than_32 or tma_cross_attention or config5" > gpurun_out/pytest_unvalidated.log 2>&1
 tail -15 gpurun_out/pytest_unvalidated.log
 timeout 500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
