@@ -86,6 +86,9 @@ SIGNATURES = {
     'alm_post_omni_json': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_char_p, C.c_long, C.c_long, C.c_char_p, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t)]),
+    'alm_post_omni_kie_json': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                         C.c_long, C.c_long, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     'alm_post_mgp_fuse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_int,
                                     C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p, C.c_void_p]),

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <charconv>
 #include <string>
 #include <vector>
@@ -307,6 +308,88 @@ int alm_post_omni_json(const int64_t* pt, const int64_t* poly, const int64_t* re
     *needed = s.size() + 1;
     POST_REQUIRE(json && cap >= s.size() + 1, "alm_post_omni_json: buffer too small (see *needed)");
     memcpy(json, s.c_str(), s.size() + 1);
+  });
+}
+
+int alm_post_omni_kie_json(const int64_t* tokens, const float* probs, int n_tok, const int32_t* inst_pos, int n_inst,
+                           const int64_t* poly, const int64_t* rec, int rec_length, int num_bins, int recog_pad_index,
+                           int rec_eos_index, const char* chars, const char* const* classes, int n_classes, int class_base,
+                           long orig_h, long orig_w, char* json, size_t cap, size_t* needed) {
+  return post_guard([&] {
+    POST_REQUIRE(n_tok >= 0 && n_inst >= 0 && rec_length > 0 && num_bins > 0 && chars && classes && needed,
+                 "alm_post_omni_kie_json: arguments");
+    POST_REQUIRE(n_tok == 0 || (tokens && probs), "alm_post_omni_kie_json: null token buffers");
+    POST_REQUIRE(n_inst == 0 || (inst_pos && poly && rec), "alm_post_omni_kie_json: null instance buffers");
+    const std::string cs(chars);
+    const auto spans = utf8_spans(cs);
+    // the walk of decode_vie_pt_poly_rec_seq (transformer.py:148-215): an (x, y) pair of bins is a word (its polygon
+    // extent and transcription were decoded by the batched poly / rec loops), a lone bin is skipped, any other token
+    // is an entity class and closes the entity collected so far
+    std::string out = "[";
+    std::vector<std::string> words;
+    std::vector<double> rects;
+    bool first_entity = true;
+    int next_inst = 0;
+    for (int i = 0; i < n_tok;) {
+      const int64_t tk = tokens[i];
+      if (tk < num_bins) {
+        if (i + 1 <= n_tok - 1 && tokens[i + 1] < num_bins) {
+          POST_REQUIRE(next_inst < n_inst && inst_pos[next_inst] == i,
+                       "alm_post_omni_kie_json: instance list does not match the (x, y) pairs of the token stream");
+          const int64_t* pp = poly + static_cast<size_t>(next_inst) * 32;
+          int64_t mnx = pp[0], mxx = pp[0], mny = pp[1], mxy = pp[1];
+          for (int k = 0; k < 16; ++k) {
+            mnx = std::min(mnx, pp[2 * k]); mxx = std::max(mxx, pp[2 * k]);
+            mny = std::min(mny, pp[2 * k + 1]); mxy = std::max(mxy, pp[2 * k + 1]);
+          }
+          // image_w.item() * min.item() / num_bins: exact integer product, then one double division (:165-168)
+          rects.push_back(static_cast<double>(orig_w * mnx) / num_bins);
+          rects.push_back(static_cast<double>(orig_h * mny) / num_bins);
+          rects.push_back(static_cast<double>(orig_w * mxx) / num_bins);
+          rects.push_back(static_cast<double>(orig_h * mxy) / num_bins);
+          std::string w;
+          for (int j = 0; j < rec_length; ++j) {
+            const int64_t id = rec[static_cast<size_t>(next_inst) * rec_length + j];
+            if (id == recog_pad_index || id == rec_eos_index) break;
+            if (id == recog_pad_index - 1) continue;
+            int64_t ci = id - num_bins;
+            const int64_t ncs = static_cast<int64_t>(spans.size());
+            if (ci < 0) ci += ncs;
+            POST_REQUIRE(ci >= 0 && ci < ncs, "alm_post_omni_kie_json: recognition id has no character");
+            w.append(cs, spans[static_cast<size_t>(ci)].first, spans[static_cast<size_t>(ci)].second);
+          }
+          words.push_back(w);
+          ++next_inst;
+          i += 2;
+        } else {
+          i += 1;
+        }
+        continue;
+      }
+      const int64_t cls = tk - class_base;
+      POST_REQUIRE(cls >= 0 && cls < n_classes, "alm_post_omni_kie_json: token is neither a bin nor an entity class (KeyError in the reference)");
+      std::string text;
+      for (size_t k = 0; k < words.size(); ++k) {
+        if (k) text += ' ';
+        text += words[k];
+      }
+      if (!first_entity) out += ", ";
+      first_entity = false;
+      out += "[" + json_string(text) + ", " + json_string(classes[cls]) + ", " + py_float_repr(static_cast<double>(probs[i])) + ", [";
+      for (size_t k = 0; k < rects.size(); k += 4) {
+        if (k) out += ", ";
+        out += "[" + py_float_repr(rects[k]) + ", " + py_float_repr(rects[k + 1]) + ", " + py_float_repr(rects[k + 2]) + ", " +
+               py_float_repr(rects[k + 3]) + "]";
+      }
+      out += "]]";
+      words.clear();
+      rects.clear();
+      i += 1;
+    }
+    out += "]";
+    *needed = out.size() + 1;
+    POST_REQUIRE(json && cap >= out.size() + 1, "alm_post_omni_kie_json: buffer too small (see *needed)");
+    memcpy(json, out.c_str(), out.size() + 1);
   });
 }
 

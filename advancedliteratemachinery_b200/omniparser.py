@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
+from types import SimpleNamespace
 from typing import List, Optional
 
 import numpy as np
@@ -217,6 +218,24 @@ class OmniParserB200:
                     i += 1
             results.append(out)
         return results
+
+    def kie_results_json(self, image_sizes) -> List[Optional[str]]:
+        """The text `json.dump(output, f)` stores per image (engine/val.py:38-42) for the last `decode_kie` call, produced
+        by the library's C++ entity walk (`alm_post_omni_kie_json`); None where nothing was decoded."""
+        from . import postprocess
+        raw, v = self.last_kie_raw, self.vocab
+        args = SimpleNamespace(chars=v.chars, num_bins=v.num_bins, rec_length=v.rec_length,
+                               recog_pad_index=v.recog_pad_index, rec_eos_index=v.rec_eos_index)
+        out = []
+        for b in range(len(raw['n_tok'])):
+            nt, ni = int(raw['n_tok'][b]), int(raw['n_inst'][b])
+            if nt == 0:
+                out.append(None)
+                continue
+            out.append(postprocess.kie_json(raw['tokens'][b, :nt], raw['probs'][b, :nt], raw['inst_pos'][b, :ni],
+                                            raw['poly'][b, :ni], raw['rec'][b, :ni], image_sizes[b], args, v.classes,
+                                            v.padding_index + 1))
+        return out
 
     def decode_logits(self, image: int, kind: str, seq: torch.Tensor) -> torch.Tensor:
         """Teacher-forced ``Transformer.decode`` (model/transformer.py:74-100): seq [n,len] -> [n,len,V]."""

@@ -87,6 +87,32 @@ def results_json(index_seqs, prob_seqs, target, args) -> str:
     return buf.value.decode('utf-8')
 
 
+def kie_json(tokens, probs, inst_pos, poly, rec, image_size, args, classes: Sequence[str], class_base: int) -> str:
+    """`json.dumps(output)` of the reference's KIE result for one image (model/transformer.py:148-215,
+    engine/val.py:38-42) from the raw outputs of `alm_omni_decode_kie` (`OmniParserB200.last_kie_raw`, one image):
+    tokens / probs [n_tok], inst_pos [n_inst], poly [n_inst, 32], rec [n_inst, rec_length]; image_size = (h, w)."""
+    lib = _lib.load()
+    tokens = np.ascontiguousarray(tokens, dtype=np.int64)
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    inst_pos = np.ascontiguousarray(inst_pos, dtype=np.int32)
+    poly = np.ascontiguousarray(poly, dtype=np.int64)
+    rec = np.ascontiguousarray(rec, dtype=np.int64)
+    table = _table(classes)
+    need = C.c_size_t(0)
+    cap = 1 << 16
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        rc = lib.alm_post_omni_kie_json(tokens.ctypes.data, probs.ctypes.data, tokens.size, inst_pos.ctypes.data, inst_pos.size,
+                                        poly.ctypes.data, rec.ctypes.data, args.rec_length, args.num_bins, args.recog_pad_index,
+                                        args.rec_eos_index, args.chars.encode('utf-8'), table, len(classes), class_base,
+                                        int(image_size[0]), int(image_size[1]), C.addressof(buf), cap, C.byref(need))
+        if rc == 0 or need.value <= cap:
+            break
+        cap = need.value
+    _check(rc)
+    return buf.value.decode('utf-8')
+
+
 def _table(tokens: Sequence) -> "C.Array":
     enc = [t if isinstance(t, bytes) else str(t).encode('utf-8') for t in tokens]
     return (C.c_char_p * len(enc))(*enc)

@@ -249,6 +249,17 @@ ALM_API int alm_post_omni_json(const int64_t* pt, const int64_t* poly, const int
                                int rec_length, int num_bins, int recog_pad_index, int rec_eos_index, const char* chars,
                                long orig_h, long orig_w, const char* image_id, char* json, size_t cap, size_t* needed);
 
+/* KIE: the entity walk of decode_vie_pt_poly_rec_seq (OCR/OmniParser/model/transformer.py:148-215) over ONE image's
+ * outputs of alm_omni_decode_kie (tokens / probs [n_tok], inst_pos [n_inst], poly [n_inst,32], rec [n_inst,rec_length]),
+ * written as the JSON text `json.dump(output, f)` stores (engine/val.py:38-42):
+ * [[text, class_name, prob, [[x0, y0, x1, y1], ...]], ...].  classes[i] names token id class_base + i
+ * (class_base = padding_index + 1, transformer.py:54-61).  Size protocol as alm_post_omni_json. */
+ALM_API int alm_post_omni_kie_json(const int64_t* tokens, const float* probs, int n_tok, const int32_t* inst_pos, int n_inst,
+                                   const int64_t* poly, const int64_t* rec, int rec_length, int num_bins,
+                                   int recog_pad_index, int rec_eos_index, const char* chars, const char* const* classes,
+                                   int n_classes, int class_base, long orig_h, long orig_w, char* json, size_t cap,
+                                   size_t* needed);
+
 /* MGP-STR A^3 fusion (OCR/MGP-STR/test_final.py:176-240, demo.py:36-112, utils.py:52-87) for B crops.
  *   ids / prob: [3][B,T] int32 top-1 ids and f32 max-softmax probabilities of the char, bpe and wp heads INCLUDING
  *   position 0 (exactly what alm_mgpstr_forward returns; T = 27).

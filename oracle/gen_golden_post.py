@@ -2,6 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY (build container: needs /root/reference).  Usage:
     python -m oracle.gen_golden_post omni
+    python -m oracle.gen_golden_post kie
     python -m oracle.gen_golden_post mgp
 (two interpreters: both reference sub-projects define a top-level `utils`).
 """
@@ -82,6 +83,88 @@ def gen_omni():
     print('post_omni.json:', len(out), 'cases,', sum(len(o['results']) for o in out), 'instances')
 
 
+def kie_case(seed, n_tok, rec_length, orig, chars=CHARS, vie=4):
+    """A random KIE point-token stream (bins, lone bins, class tokens) + the polygon / transcription ids of every
+    (x, y) pair in it."""
+    g = torch.Generator().manual_seed(seed)
+    a = omni_args(chars, rec_length)
+    a.pt_sos_index = a.rec_eos_index + 1
+    a.padding_index = a.pt_sos_index + 3                      # utils/parser.py:98-103
+    a.vie_categories = vie
+    base = a.padding_index + 1
+    toks, i = [], 0
+    while len(toks) < n_tok:
+        r = float(torch.rand(1, generator=g))
+        if r < 0.55 and len(toks) + 2 <= n_tok:
+            toks += torch.randint(0, a.num_bins, (2,), generator=g).tolist()
+        elif r < 0.7:
+            toks.append(int(torch.randint(0, a.num_bins, (1,), generator=g)))
+            toks.append(base + int(torch.randint(0, vie, (1,), generator=g)))   # lone bin, then a class token
+        else:
+            toks.append(base + int(torch.randint(0, vie, (1,), generator=g)))
+    toks = toks[:n_tok]
+    pos = []
+    i = 0
+    while i < len(toks):
+        if toks[i] < a.num_bins and i + 1 <= len(toks) - 1 and toks[i + 1] < a.num_bins:
+            pos.append(i)
+            i += 2
+        else:
+            i += 1
+    n = len(pos)
+    poly = torch.randint(0, a.num_bins, (n, 32), generator=g)
+    rec = torch.randint(a.num_bins, a.recog_pad_index - 1, (n, rec_length), generator=g)
+    for k in range(n):
+        cut = int(torch.randint(0, rec_length + 1, (1,), generator=g))
+        if cut < rec_length:
+            rec[k, cut] = a.rec_eos_index if k % 2 else a.recog_pad_index
+        if k % 3 == 0:
+            rec[k, int(torch.randint(0, rec_length, (1,), generator=g))] = a.recog_pad_index - 1
+    probs = torch.rand(len(toks), generator=g)
+    return dict(tokens=toks, probs=probs, pos=pos, poly=poly, rec=rec, orig=orig, args=a, base=base)
+
+
+def gen_kie():
+    """Pins the KIE entity walk against the reference's own decode_vie_pt_poly_rec_seq: the method is called unbound on
+    a stub `self` whose `decode` is scripted to emit the prepared polygon / transcription ids, so every line of the
+    reference walk (pair detection, extents, transcription, class lookup, entity closing) runs unmodified."""
+    sys.path[:0] = [os.path.join(REPO, 'oracle', 'shim'), os.path.join(REF, 'OmniParser')]
+    sys.modules.setdefault('bezier', types.ModuleType('bezier'))
+    from model.transformer import Transformer                # the reference class, unmodified
+    from oracle.postprocess_ref import kie_walk
+    classes = ['company', 'date', 'address', 'total']         # SROIE (transformer.py:58-61)
+    cases = [kie_case(21, 30, 25, (480, 640)), kie_case(22, 9, 25, (1000, 333)), kie_case(23, 64, 7, (2160, 3840)),
+             kie_case(24, 1, 25, (10, 10)), kie_case(25, 40, 25, (777, 555), chars=CHARS[:50] + '\u00e9\u4e2d' + CHARS[52:])]
+    out = []
+    for c in cases:
+        a = c['args']
+        V = a.padding_index + 1 + a.vie_categories
+        state = {'inst': -1}
+
+        def decode(seq, memory, mask, pos_embed, kind, c=c, state=state, V=V):
+            step = seq.shape[1] - 3
+            if kind == 'poly' and step == 0:
+                state['inst'] += 1
+            target = int((c['poly'] if kind == 'poly' else c['rec'])[state['inst'], step])
+            lg = torch.full((1, seq.shape[1], V), -30.0)
+            lg[:, :, target] = 30.0
+            return lg
+
+        stub = types.SimpleNamespace(args=a, decode=decode,
+                                     index2class={c['base'] + i: n for i, n in enumerate(classes)})
+        pt_seq = torch.tensor(c['tokens'], dtype=torch.long)
+        ref = Transformer.decode_vie_pt_poly_rec_seq(stub, pt_seq, c['probs'], torch.tensor([[a.rec_eos_index - 1]]),
+                                                     torch.tensor([[a.rec_eos_index]]), torch.tensor(c['orig']), None, None, None)
+        mine = kie_walk(c['tokens'], c['probs'], c['pos'], c['poly'], c['rec'], c['orig'], a, classes, c['base'])
+        assert json.dumps(ref) == json.dumps(mine), 'restatement differs from the reference walk'
+        out.append({'tokens': c['tokens'], 'probs_f32_hex': c['probs'].numpy().astype('<f4').tobytes().hex(), 'pos': c['pos'],
+                    'poly': c['poly'].tolist(), 'rec': c['rec'].tolist(), 'orig': list(c['orig']), 'chars': a.chars,
+                    'rec_length': a.rec_length, 'classes': classes, 'class_base': c['base'], 'json': json.dumps(ref)})
+    with open(os.path.join(GOLD, 'post_kie.json'), 'w') as f:
+        json.dump(out, f)
+    print('post_kie.json:', len(out), 'cases,', sum(len(json.loads(o['json'])) for o in out), 'entities')
+
+
 def bytes_to_unicode():
     """GPT-2's published byte <-> printable-unicode table (the tokenizer's vocab strings use it)."""
     bs = list(range(ord('!'), ord('~') + 1)) + list(range(0xA1, 0xAD)) + list(range(0xAE, 0x100))
@@ -159,9 +242,11 @@ if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which == 'all':
         import subprocess
-        for w in ('omni', 'mgp'):
+        for w in ('omni', 'kie', 'mgp'):
             subprocess.check_call([sys.executable, '-m', 'oracle.gen_golden_post', w], cwd=REPO)
     elif which == 'omni':
         gen_omni()
+    elif which == 'kie':
+        gen_kie()
     else:
         gen_mgp()

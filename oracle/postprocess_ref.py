@@ -41,6 +41,39 @@ def omni_results(index_seqs, prob_seqs, file_name, orig_size, args):
     return out
 
 
+def kie_walk(tokens, probs, inst_pos, poly, rec, orig_size, args, classes, class_base):
+    """decode_vie_pt_poly_rec_seq (transformer.py:148-215) with the per-instance poly / rec decode loops replaced by the
+    already decoded ids (what the batched GPU loops return): tokens / probs of the point sequence, inst_pos = start index
+    of every (x, y) pair, poly [n,32], rec [n,L]."""
+    image_h, image_w = int(orig_size[0]), int(orig_size[1])
+    result, words, rects = [], [], []
+    by_pos = {int(p): k for k, p in enumerate(inst_pos)}
+    i = 0
+    while i < len(tokens):
+        if tokens[i] < args.num_bins:
+            if i + 1 <= len(tokens) - 1 and tokens[i + 1] < args.num_bins:
+                k = by_pos[i]
+                pts = torch.as_tensor(poly[k]).reshape(-1, 2)
+                rects.append([image_w * pts[:, 0].min().item() / args.num_bins, image_h * pts[:, 1].min().item() / args.num_bins,
+                              image_w * pts[:, 0].max().item() / args.num_bins, image_h * pts[:, 1].max().item() / args.num_bins])
+                chars = []
+                for t in torch.as_tensor(rec[k]).tolist():
+                    if t == args.recog_pad_index or t == args.rec_eos_index:
+                        break
+                    if t == args.recog_pad_index - 1:
+                        continue
+                    chars.append(args.chars[t - args.num_bins])
+                words.append(''.join(chars))
+                i += 2
+            else:
+                i += 1
+        else:
+            result.append((' '.join(words), classes[tokens[i] - class_base], torch.as_tensor(probs)[i].item(), rects))
+            words, rects = [], []
+            i += 1
+    return result
+
+
 def mgp_fuse_ref(strings, ids, prob):
     """test_final.py:176-240 for one batch.  strings: [3][B] the converter's decoded strings (char / bpe / wp);
     ids, prob: [3, B, T] incl. position 0.  Returns texts [3][B], conf [3][B] (float), fused [B], source [B]."""

@@ -332,6 +332,10 @@ def test_kie_decode_matches_reference_fixture(golden_dir):
     raw = m.last_kie_raw
     assert np.array_equal(raw['tokens'][0, :raw['n_tok'][0]], gold['pt_seq'])
     np.testing.assert_allclose(raw['probs'][0, :raw['n_tok'][0]], gold['pt_probs'][:raw['n_tok'][0]], rtol=2e-3)
+    # the C++ entity walk (alm_post_omni_kie_json) on the same raw outputs == the adapter's list
+    import json
+    js = m.kie_results_json([case['canvas']])
+    assert json.loads(js[0]) == [[r[0], r[1], r[2], r[3]] for r in out]
     m.ctx.close()
 
 

@@ -91,3 +91,34 @@ def test_mgp_fusion_equals_reference():
     assert out['fused'] == c['fused']
     assert out['source'].tolist() == c['source']
     assert -1 in c['source'] and {0, 1, 2} <= set(c['source'])   # the fixture exercises every branch
+
+
+def test_kie_walk_json_equals_reference():
+    """alm_post_omni_kie_json == json.dumps of the reference's own decode_vie_pt_poly_rec_seq (run unbound with a scripted
+    decode stub, oracle/gen_golden_post.py): pair detection, lone bins, polygon extents, transcriptions, class lookup,
+    entity closing, an unfinished trailing entity, an entity without words, unicode characters."""
+    cases = json.load(open(os.path.join(GOLD, 'post_kie.json')))
+    assert len(cases) == 5
+    seen_empty_entity = False
+    for c in cases:
+        a = types.SimpleNamespace(chars=c['chars'], num_bins=1000, rec_length=c['rec_length'])
+        a.recog_pad_index = a.num_bins + len(a.chars) + 1
+        a.rec_eos_index = a.recog_pad_index + 3
+        probs = np.frombuffer(bytes.fromhex(c['probs_f32_hex']), dtype='<f4').copy()
+        text = P.kie_json(c['tokens'], probs, c['pos'], np.asarray(c['poly'], dtype=np.int64).reshape(-1, 32),
+                          np.asarray(c['rec'], dtype=np.int64).reshape(-1, a.rec_length), c['orig'], a, c['classes'],
+                          c['class_base'])
+        assert text == c['json']
+        seen_empty_entity |= any(e[0] == '' and e[3] == [] for e in json.loads(text))
+    assert seen_empty_entity
+
+
+def test_kie_walk_rejects_inconsistent_input():
+    from advancedliteratemachinery_b200 import AlmError
+    a = types.SimpleNamespace(chars='ab', num_bins=1000, rec_length=2, recog_pad_index=1003, rec_eos_index=1006)
+    with pytest.raises(AlmError):          # an (x, y) pair in the stream but no decoded instance for it
+        P.kie_json([1, 2, 1011], np.ones(3, dtype=np.float32), [], np.zeros((0, 32)), np.zeros((0, 2)), (10, 10), a,
+                   ['c0', 'c1', 'c2', 'c3'], 1011)
+    with pytest.raises(AlmError):          # a token that is neither a bin nor a class (KeyError in the reference)
+        P.kie_json([1005], np.ones(1, dtype=np.float32), [], np.zeros((0, 32)), np.zeros((0, 2)), (10, 10), a,
+                   ['c0'], 1011)
