@@ -15,7 +15,7 @@ build/%.o: $(SRC_DIR)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
 $(OUT): $(OBJS)
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -cudart static
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -cudart static -ldl
 
 clean:
 	rm -rf build $(OUT)

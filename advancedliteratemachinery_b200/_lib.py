@@ -52,6 +52,14 @@ SIGNATURES = {
                                     C.POINTER(C.c_float), C.c_void_p]),
     'alm_bench_gemm': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     'alm_load_weights': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TensorDesc), C.c_int]),
+    'alm_share_weights': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'alm_stream_wait': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'alm_stream_release': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'alm_comm_unique_id': (C.c_int, [C.c_void_p]),
+    'alm_comm_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'alm_comm_attach': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'alm_broadcast_weights': (C.c_int, [C.c_void_p, C.c_int]),
+    'alm_gather_sequences': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'alm_omni_encode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'alm_omni_get_feature': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     'alm_omni_get_memory': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
+#include <memory>
 #include <tuple>
 #include <unordered_map>
 #include <string>
@@ -57,6 +59,15 @@ struct Arena {
   size_t mark() const { return off; }
   void release(size_t m) { off = m; }
 };
+// releases the arena back to the mark on every exit path (exceptions included)
+struct ArenaScope {
+  Arena& a;
+  size_t mk;
+  explicit ArenaScope(Arena& arena) : a(arena), mk(arena.off) {}
+  ~ArenaScope() { a.release(mk); }
+  ArenaScope(const ArenaScope&) = delete;
+  ArenaScope& operator=(const ArenaScope&) = delete;
+};
 
 // K-major bf16 operand (hi/lo split pair), optionally batched over two batch dims.
 struct Operand {
@@ -101,6 +112,7 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E);
 // ---------------------------------------------------------------------------------------------
 struct HostTensor {
   std::vector<float> f32;  // converted to fp32 on load
+  bool placeholder = false;  // shape-only entry (data == NULL): zeros now, real values arrive by alm_broadcast_weights
   std::vector<int64_t> shape;
   size_t numel() const { return f32.size(); }
 };
@@ -122,6 +134,21 @@ struct MgpModel;
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Device slabs holding the converted weights.  Shared (ref-counted) between the contexts of one GPU that serve the
+// same model (alm_share_weights): one copy of the ~0.9 GB of planes, any number of execution contexts.
+struct WeightStore {
+  int device = 0;
+  std::vector<void*> slabs;
+  std::vector<size_t> used;  // bytes bump-allocated in each slab (the weight broadcast sends exactly these)
+  ~WeightStore() {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (void* p : slabs) cudaFree(p);
+    cudaSetDevice(cur);
+  }
+};
 
 struct Ctx {
   int device = 0;
@@ -172,6 +199,7 @@ struct Ctx {
   bool skipped(int bit) const { return skip_scope && (debug_skip & bit); }
   cudaStream_t stream_hi = nullptr;  // internal high-priority stream for the decode loops
   cudaEvent_t ev_prio = nullptr;
+  cudaEvent_t ev_order = nullptr;  // alm_stream_wait / alm_stream_release
   cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync event: host waits that sleep instead of spinning
   int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
@@ -193,7 +221,14 @@ struct Ctx {
   std::vector<GemmRec> gemm_recs;
   OmniModel* omni = nullptr;
   MgpModel* mgp = nullptr;
-  std::vector<void*> weight_slabs;
+  std::shared_ptr<WeightStore> wstore;
+  // multi-GPU (comm.cu): an NCCL communicator (created by alm_comm_init or attached), used for ONE weight broadcast
+  // at start-up and ONE all-gather of decoded sequences per batch
+  void* comm = nullptr;
+  bool own_comm = false;
+  int comm_rank = 0, comm_world = 1;
+  void* gather_buf = nullptr;
+  size_t gather_cap = 0;
   // weight slab bump allocator
   char* wbase = nullptr;
   size_t wcap = 0, woff = 0;
@@ -236,6 +271,22 @@ void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, 
 void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint8_t* kpm, int rows_per_mask,
                   long mask_ld, float* out_f32, bf16* out_hi, bf16* out_lo, long ldo);
 
+// Kernel attributes (dynamic shared-memory opt-in, carve-out) are per DEVICE, and one process may hold a context per
+// GPU, each driven by its own host thread: a once-flag must therefore be per device ordinal, not per process.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};  // bit d = attributes already set on device d (ordinals < 64)
+  bool need() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return ((done.load(std::memory_order_acquire) >> (d & 63)) & 1ull) == 0;
+  }
+  void mark() {
+    int d = 0;
+    cudaGetDevice(&d);
+    done.fetch_or(1ull << (d & 63), std::memory_order_release);
+  }
+};
+
 // Every kernel of the per-token decode loop asks for the same (maximum) shared-memory carve-out: consecutive kernels
 // with different L1/shared splits force an SM reconfiguration (the SM must drain) between every pair of launches.
 template <class F>
@@ -244,12 +295,20 @@ inline void pin_carveout(F* kernel) {
 }
 #define ALM_PIN_CARVEOUT(kernel)            \
   do {                                      \
-    static bool pinned_ = false;            \
-    if (!pinned_) {                         \
+    static alm::DeviceOnce pinned_;         \
+    if (pinned_.need()) {                   \
       alm::pin_carveout(kernel);            \
-      pinned_ = true;                       \
+      pinned_.mark();                       \
     }                                       \
   } while (0)
+
+// comm.cu
+void comm_unique_id(void* id128);
+void comm_init(Ctx* c, const void* id128, int rank, int world);
+void comm_attach(Ctx* c, void* nccl_comm, int rank, int world);
+void comm_release(Ctx* c);
+void comm_broadcast_weights(Ctx* c, int root);
+void comm_gather(Ctx* c, const void* send, size_t bytes, void* recv_host);
 
 void count_launch(Ctx* c, int n = 1);
 void check_launch(const char* what);

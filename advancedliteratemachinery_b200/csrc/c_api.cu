@@ -141,7 +141,9 @@ void alm_free(alm_ctx* h) {
   cudaStreamSynchronize(h->c.stream);
   delete h->c.omni;
   mgp_free(h->c.mgp);
-  for (void* p : h->c.weight_slabs) cudaFree(p);
+  comm_release(&h->c);
+  if (h->c.gather_buf) cudaFree(h->c.gather_buf);
+  h->c.wstore.reset();  // frees the slabs when this was the last context using them
   if (h->c.ws.base) cudaFree(h->c.ws.base);
   if (h->dev_in) cudaFree(h->dev_in);
   if (h->dev_mask) cudaFree(h->dev_mask);
@@ -149,6 +151,7 @@ void alm_free(alm_ctx* h) {
   if (h->c.stream_hi) cudaStreamDestroy(h->c.stream_hi);
   if (h->c.ev_prio) cudaEventDestroy(h->c.ev_prio);
   if (h->c.ev_block) cudaEventDestroy(h->c.ev_block);
+  if (h->c.ev_order) cudaEventDestroy(h->c.ev_order);
   if (h->c.ev_fork) { cudaEventDestroy(h->c.ev_fork); cudaEventDestroy(h->c.ev_join); }
   for (auto e : h->c.ev_t) if (e) cudaEventDestroy(e);
   if (h->c.own_stream) cudaStreamDestroy(h->c.stream);
@@ -266,7 +269,7 @@ int alm_bench_graph_floor(alm_ctx* h, int nodes, int iters, float* us_per_node) 
     ALM_REQUIRE(nodes > 0 && iters > 0 && us_per_node, ALM_ERR_INVALID, "alm_bench_graph_floor arguments");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     int* p = c->ws.get<int>(4);
     ALM_CHECK_CUDA(cudaMemsetAsync(p, 0, 16, c->stream));
     cudaGraph_t g = nullptr;
@@ -288,7 +291,6 @@ int alm_bench_graph_floor(alm_ctx* h, int nodes, int iters, float* us_per_node) 
     ALM_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *us_per_node = ms * 1e3f / (static_cast<float>(iters) * nodes);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(ge);
-    c->ws.release(mk);
   });
 }
 
@@ -299,7 +301,7 @@ int alm_bench_gemm_ex(alm_ctx* h, int M, int N, int K, int batch, int split_out,
                 "alm_bench_gemm_ex arguments");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     const size_t na = static_cast<size_t>(batch) * M * K, nb = static_cast<size_t>(batch) * N * K;
     const int ldo = (N + 7) & ~7;
     Operand a, b;
@@ -329,7 +331,6 @@ int alm_bench_gemm_ex(alm_ctx* h, int M, int N, int K, int batch, int split_out,
     *ms_per_launch = ms / iters;
     if (detail_out && c->detail_buf)
       ALM_CHECK_CUDA(cudaMemcpy(detail_out, c->detail_buf, 64 * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    c->ws.release(mk);
   });
 }
 
@@ -339,7 +340,7 @@ int alm_bench_gemm(alm_ctx* h, int M, int N, int K, int iters, float* ms_per_lau
                 "alm_bench_gemm arguments");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     float* fa = c->ws.get<float>(static_cast<size_t>(M) * K);
     float* fb = c->ws.get<float>(static_cast<size_t>(N) * K);
     // any finite data does; reuse whatever the arena holds after clamping it through a split
@@ -368,7 +369,6 @@ int alm_bench_gemm(alm_ctx* h, int M, int N, int K, int iters, float* ms_per_lau
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_per_launch = ms / iters;
-    c->ws.release(mk);
   });
 }
 
@@ -378,7 +378,7 @@ int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors,
     std::map<std::string, HostTensor> t;
     for (int i = 0; i < n; ++i) {
       const alm_tensor_desc& d = tensors[i];
-      ALM_REQUIRE(d.name && d.data && d.ndim >= 0 && d.ndim <= 4, ALM_ERR_INVALID, "bad tensor descriptor");
+      ALM_REQUIRE(d.name && d.ndim >= 0 && d.ndim <= 4, ALM_ERR_INVALID, "bad tensor descriptor");
       HostTensor ht;
       size_t numel = 1;
       for (int k = 0; k < d.ndim; ++k) {
@@ -386,6 +386,11 @@ int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors,
         numel *= static_cast<size_t>(d.shape[k]);
       }
       ht.f32.resize(numel);
+      if (d.data == nullptr) {  // shape-only placeholder (non-root ranks before alm_broadcast_weights)
+        ht.placeholder = true;
+        t.emplace(d.name, std::move(ht));
+        continue;
+      }
       switch (d.dtype) {
         case ALM_F32: memcpy(ht.f32.data(), d.data, numel * 4); break;
         case ALM_F16:
@@ -410,6 +415,69 @@ int alm_load_weights(alm_ctx* h, int model_kind, const alm_tensor_desc* tensors,
 
 int alm_synchronize(alm_ctx* h) {
   return guarded(h, [&] { ALM_CHECK_CUDA(cudaStreamSynchronize(h->c.stream)); });
+}
+
+// ------------------------------------------------------------------------------------------ sharing / streams / comm
+int alm_share_weights(alm_ctx* h, alm_ctx* owner) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(owner && owner != h, ALM_ERR_INVALID, "alm_share_weights: owner context");
+    ALM_REQUIRE(owner->c.device == h->c.device, ALM_ERR_INVALID, "alm_share_weights: contexts are on different devices");
+    ALM_REQUIRE(owner->c.wstore && (owner->c.omni || owner->c.mgp), ALM_ERR_STATE, "alm_share_weights: owner has no weights");
+    delete h->c.omni;
+    h->c.omni = nullptr;
+    mgp_free(h->c.mgp);
+    h->c.mgp = nullptr;
+    h->c.wstore = owner->c.wstore;  // ref-counted: the slabs live until the last context using them is freed
+    h->c.wbase = nullptr; h->c.wcap = 0; h->c.woff = 0;
+    if (owner->c.omni) h->c.omni = omni_share(owner->c.omni);
+    if (owner->c.mgp) h->c.mgp = mgp_share(owner->c.mgp);
+  });
+}
+
+int alm_stream_wait(alm_ctx* h, void* producer_stream) {
+  return guarded(h, [&] {
+    Ctx* c = &h->c;
+    if (!c->ev_order) ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    ALM_CHECK_CUDA(cudaEventRecord(c->ev_order, static_cast<cudaStream_t>(producer_stream)));
+    ALM_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_order, 0));
+  });
+}
+
+int alm_stream_release(alm_ctx* h, void* consumer_stream) {
+  return guarded(h, [&] {
+    Ctx* c = &h->c;
+    if (!c->ev_order) ALM_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    ALM_CHECK_CUDA(cudaEventRecord(c->ev_order, c->stream));
+    ALM_CHECK_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(consumer_stream), c->ev_order, 0));
+  });
+}
+
+int alm_comm_unique_id(void* id128) {
+  if (!id128) return ALM_ERR_INVALID;
+  try {
+    comm_unique_id(id128);
+    return ALM_OK;
+  } catch (const AlmError& e) {
+    return e.code;
+  } catch (...) {
+    return ALM_ERR_INVALID;
+  }
+}
+
+int alm_comm_init(alm_ctx* h, const void* id128, int rank, int world) {
+  return guarded(h, [&] { comm_init(&h->c, id128, rank, world); });
+}
+
+int alm_comm_attach(alm_ctx* h, void* nccl_comm, int rank, int world) {
+  return guarded(h, [&] { comm_attach(&h->c, nccl_comm, rank, world); });
+}
+
+int alm_broadcast_weights(alm_ctx* h, int root) {
+  return guarded(h, [&] { comm_broadcast_weights(&h->c, root); });
+}
+
+int alm_gather_sequences(alm_ctx* h, const void* send, size_t bytes_per_rank, void* recv_host) {
+  return guarded(h, [&] { comm_gather(&h->c, send, bytes_per_rank, recv_host); });
 }
 
 // ------------------------------------------------------------------------------------------ pre-processing
@@ -466,7 +534,7 @@ int alm_pre_omni_pages(alm_ctx* h, const uint8_t* const* rgb, const int* heights
     ALM_REQUIRE(is_device_ptr(tensors) && is_device_ptr(mask), ALM_ERR_INVALID, "outputs must be device buffers");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     std::vector<PreImage> imgs = stage_images(h, rgb, heights, widths, n);
     int Hc = 0, Wc = 0;
     for (auto& im : imgs) {
@@ -475,7 +543,6 @@ int alm_pre_omni_pages(alm_ctx* h, const uint8_t* const* rgb, const int* heights
       Wc = std::max(Wc, im.ow);
     }
     pre_resize_batch(c, imgs, PRE_BILINEAR, true, tensors, Hc, Wc, mask);
-    c->ws.release(mk);
   });
 }
 
@@ -487,11 +554,10 @@ int alm_pre_mgp_crops(alm_ctx* h, const uint8_t* const* rgb, const int* heights,
     ALM_REQUIRE(is_device_ptr(out), ALM_ERR_INVALID, "output must be a device buffer");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     std::vector<PreImage> imgs = stage_images(h, rgb, heights, widths, n);
     for (auto& im : imgs) { im.oh = imgH; im.ow = imgW; }
     pre_resize_batch(c, imgs, PRE_BICUBIC, false, out, imgH, imgW, nullptr);
-    c->ws.release(mk);
   });
 }
 
@@ -599,7 +665,7 @@ int alm_op_linear(alm_ctx* h, const float* A, const float* W, const float* bias,
     ALM_REQUIRE(is_device_ptr(A) && is_device_ptr(W) && is_device_ptr(C), ALM_ERR_INVALID, "device pointers required");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     const int Kp = (K + 7) & ~7;
     bf16* ah = c->ws.get<bf16>(static_cast<size_t>(batch) * M * Kp);
     bf16* al = c->ws.get<bf16>(static_cast<size_t>(batch) * M * Kp);
@@ -622,7 +688,6 @@ int alm_op_linear(alm_ctx* h, const float* A, const float* W, const float* bias,
     e.bias = bias; e.bias_mode = bias ? BIAS_COL : BIAS_NONE; e.act = act;
     gemm(c, a, b, e);
     ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-    c->ws.release(mk);
   });
 }
 
@@ -642,7 +707,7 @@ int alm_op_window_attention(alm_ctx* h, const float* qkv, const float* bias_tabl
     ALM_REQUIRE(qkv && bias_table && out, ALM_ERR_INVALID, "alm_op_window_attention arguments");
     Ctx* c = &h->c;
     c->ensure_ws();
-    const size_t mk = c->ws.mark();
+    ArenaScope arena_scope(c->ws);
     std::vector<float> tab(static_cast<size_t>(169) * heads), dense(static_cast<size_t>(heads) * 2401);
     ALM_CHECK_CUDA(cudaMemcpy(tab.data(), bias_table, tab.size() * 4, cudaMemcpyDeviceToHost));
     for (int hh = 0; hh < heads; ++hh)
@@ -654,7 +719,6 @@ int alm_op_window_attention(alm_ctx* h, const float* qkv, const float* bias_tabl
     ALM_CHECK_CUDA(cudaMemcpyAsync(dd, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, c->stream));
     window_attention(c, qkv, C, heads, nWh, nWw, B, shift, nWh * 7, nWw * 7, dd, nullptr, nullptr, out);
     ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-    c->ws.release(mk);
   });
 }
 

@@ -12,12 +12,18 @@ void* Ctx::walloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMalloc(&p, slab) != cudaSuccess)
       throw AlmError{ALM_ERR_OOM, "cudaMalloc of a " + std::to_string(slab >> 20) + " MiB weight slab failed"};
-    weight_slabs.push_back(p);
+    if (!wstore) {
+      wstore = std::make_shared<WeightStore>();
+      wstore->device = device;
+    }
+    wstore->slabs.push_back(p);
+    wstore->used.push_back(0);
     wbase = static_cast<char*>(p);
     wcap = slab;
     a = 0;
   }
   woff = a + bytes;
+  wstore->used.back() = woff;
   return wbase + a;
 }
 

@@ -489,12 +489,12 @@ const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int bo
 template <int BLOCK_N, int NSPLIT>
 void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   using L = SmemLayout<BLOCK_N, NSPLIT>;
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, NSPLIT>;
-  if (!attr_set) {
+  if (attr_set.need()) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     pin_carveout(kern);
-    attr_set = true;
+    attr_set.mark();
   }
   p.n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   p.num_tiles = static_cast<long>(p.m_blocks) * p.n_blocks * p.nb0 * p.nb1;

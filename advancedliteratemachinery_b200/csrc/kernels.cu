@@ -645,12 +645,12 @@ void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, c
   const size_t dyn = static_cast<size_t>(M) * (K <= 512 ? K : 2 * 512) * sizeof(float);
 #define ALM_GEMV(MRV, NWV)                                                                                         \
   do {                                                                                                             \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
+    static alm::DeviceOnce attr;                                                                                   \
+    if (attr.need()) {                                                                                              \
       ALM_CHECK_CUDA(cudaFuncSetAttribute(gemv_rows_kernel<MRV, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           128 * 1024));                                                            \
       alm::pin_carveout(gemv_rows_kernel<MRV, NWV>);                                                               \
-      attr = true;                                                                                                 \
+      attr.mark();                                                                                                 \
     }                                                                                                              \
     gemv_rows_kernel<MRV, NWV><<<grid, 128, dyn, c->stream>>>(x, x2 ? x2 : x, n_split, ldx, W, bias, resid, ldr,   \
                                                               out, ldo, M, N, K, act);                            \

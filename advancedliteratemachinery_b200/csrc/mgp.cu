@@ -44,6 +44,7 @@ struct MgpModel {
 };
 
 void mgp_free(MgpModel* m) { delete m; }
+MgpModel* mgp_share(const MgpModel* owner) { return new MgpModel(*owner); }
 
 namespace {
 

@@ -8,4 +8,5 @@ void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& t);
 void mgp_forward(Ctx* c, const float* img_dev, int B, float* attn, float* char_logits, float* bpe_logits,
                  float* wp_logits, int32_t* ids, float* prob);
 void mgp_free(MgpModel* m);
+MgpModel* mgp_share(const MgpModel* owner);  // weights only: a plain copy of the pointer table
 }  // namespace alm

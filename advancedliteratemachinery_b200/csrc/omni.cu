@@ -136,7 +136,7 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
       const HostTensor& tab = need(t, p + "attn.relative_position_bias_table");
       ALM_REQUIRE(static_cast<int>(tab.numel()) == 169 * heads, ALM_ERR_INVALID, "bias table shape mismatch at " + p);
       auto it = t.find(p + "attn.relative_position_index");
-      if (it != t.end()) {
+      if (it != t.end() && !it->second.placeholder) {
         ALM_REQUIRE(it->second.numel() == 49 * 49, ALM_ERR_INVALID, "relative_position_index shape at " + p);
         for (int i = 0; i < 49 * 49; ++i)
           ALM_REQUIRE(static_cast<int>(it->second.f32[i]) == rel_index[i], ALM_ERR_INVALID,
@@ -219,6 +219,19 @@ void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t) {
   m->ca_v_all.b = upload_f32(c, vb.data(), vb.size());
   delete c->omni;
   c->omni = m;
+}
+
+OmniModel* omni_share(const OmniModel* owner) {
+  OmniModel* m = new OmniModel(*owner);  // weight pointers (the slabs are ref-counted by Ctx::wstore)
+  m->step_graphs.clear();                // graphs, encode state and cache pointers belong to the owner's arena
+  m->encoded = false;
+  m->B = m->H = m->W = m->M = m->Mpad = m->mh = m->mw = 0;
+  for (auto& f : m->feat) f = nullptr;
+  m->memory = m->pos = nullptr;
+  m->kpm = nullptr;
+  m->kc_hi = m->kc_lo = m->vc_hi = m->vc_lo = m->vt_hi = m->vt_lo = nullptr;
+  m->ws_mark = 0;
+  return m;
 }
 
 // ================================================================================================ encode
@@ -699,13 +712,18 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
                       int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode before alm_omni_encode");
-  ALM_REQUIRE(c->xattn_impl == 0 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
+  ALM_REQUIRE(c->xattn_impl != 1 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
   ALM_REQUIRE(n_prompt >= 1 && n_prompt <= 16, ALM_ERR_INVALID, "pt prompt length");
-  ALM_REQUIRE(cfg.pt_seq_length >= 1 && n_prompt + cfg.pt_seq_length - 1 <= 1024, ALM_ERR_INVALID,
-              "prompt + pt_seq_length exceeds the 1024-row position table (transformer.py:475)");
+  ALM_REQUIRE(cfg.pt_seq_length >= 1, ALM_ERR_INVALID, "pt_seq_length");
+  // The reference default is --pt_seq_length 1024 (utils/parser.py:21) with a 5- or 7-token prompt: more steps than the
+  // 1024-row position table (transformer.py:475) can serve.  It works because EOS ends the loop (:126) long before
+  // step 1025 - n_prompt, where the embedding lookup (:312) would raise.  Same here: the loop is sized by the table,
+  // and an image that is still alive when the table is exhausted is an error, as in the reference.
+  const int pt_steps = std::min(cfg.pt_seq_length, 1025 - n_prompt);
+  const bool pt_clamped = pt_steps < cfg.pt_seq_length;
   ALM_REQUIRE(cfg.vie_categories == m->vie, ALM_ERR_INVALID, "vie_categories does not match the loaded checkpoint");
   ALM_REQUIRE(kie == (m->vie > 0), ALM_ERR_INVALID, "use alm_omni_decode for text spotting and alm_omni_decode_kie for KIE");
-  ALM_REQUIRE(cfg.max_instances >= (cfg.pt_seq_length / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
+  ALM_REQUIRE(cfg.max_instances >= (pt_steps / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
   ALM_REQUIRE(cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
   const int B = m->B;
   Arena& ws = c->ws;
@@ -743,9 +761,9 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[2], c->stream));
 
   // ------------------------------------------------------------------ pt loop (transformer.py:102-141)
-  const int Tpt = n_prompt + cfg.pt_seq_length;
+  const int Tpt = n_prompt + pt_steps;
   int* pt_tok = ws.get<int>(static_cast<size_t>(B) * Tpt);
-  float* pt_prob = ws.get<float>(static_cast<size_t>(B) * cfg.pt_seq_length);
+  float* pt_prob = ws.get<float>(static_cast<size_t>(B) * pt_steps);
   int* finished = ws.get<int>(B);
   int* ntok = ws.get<int>(B);
   {
@@ -765,25 +783,28 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
     run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, n_prompt - 1, off);  // prompt tokens only fill the caches
     HeadArgs h;
     h.on = true; h.cfg = hc; h.tokens = pt_tok; h.tstride = Tpt; h.n_prompt_m1 = n_prompt - 1;
-    h.probs = pt_prob; h.pstride = cfg.pt_seq_length;
+    h.probs = pt_prob; h.pstride = pt_steps;
     h.finished = finished; h.ntok = ntok; h.seqs_per_image = 1;
     std::vector<int> fin(B);
-    for (int done = 0; done < cfg.pt_seq_length;) {
-      const int chunk = std::min(16, cfg.pt_seq_length - done);
+    bool all_done = false;
+    for (int done = 0; done < pt_steps && !all_done;) {
+      const int chunk = std::min(16, pt_steps - done);
       run_steps(c, m, 0, u, pt_tok, Tpt, 0, B, chunk, h);
       done += chunk;
-      if (done < cfg.pt_seq_length) {  // every image hit EOS?  (one small sync per 16 tokens)
+      if (done < pt_steps || pt_clamped) {  // every image hit EOS?  (one small sync per 16 tokens)
         wait_stream(c, c->stream);
         ALM_CHECK_CUDA(cudaMemcpyAsync(fin.data(), finished, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-        if (std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; })) break;
+        all_done = std::all_of(fin.begin(), fin.end(), [](int v) { return v != 0; });
       }
     }
+    ALM_REQUIRE(!pt_clamped || all_done, ALM_ERR_INVALID,
+                "an image produced no EOS within the 1024-row position table (the reference raises at transformer.py:312)");
   }
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[3], c->stream));
   wait_stream(c, c->stream);
   std::vector<int> h_ntok(B), h_tok(static_cast<size_t>(B) * Tpt);
-  std::vector<float> h_prob(static_cast<size_t>(B) * cfg.pt_seq_length);
+  std::vector<float> h_prob(static_cast<size_t>(B) * pt_steps);
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_ntok.data(), ntok, B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_tok.data(), pt_tok, h_tok.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   ALM_CHECK_CUDA(cudaMemcpyAsync(h_prob.data(), pt_prob, h_prob.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -806,7 +827,7 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
       if (n_tok_out) n_tok_out[b] = len;
       for (int i = 0; i < len; ++i) {
         pt_tok_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = t[i];
-        pt_prob_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = h_prob[static_cast<size_t>(b) * cfg.pt_seq_length + i];
+        pt_prob_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = h_prob[static_cast<size_t>(b) * pt_steps + i];
       }
     }
     n_inst[b] = static_cast<int>(starts[b].size());
@@ -918,7 +939,7 @@ void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_d
 void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode_logits before alm_omni_encode");
-  ALM_REQUIRE(c->xattn_impl == 0 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
+  ALM_REQUIRE(c->xattn_impl != 1 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
   ALM_REQUIRE(image >= 0 && image < m->B && kind >= 0 && kind < 3 && n_seq > 0 && len > 0 && len <= 1024,
               ALM_ERR_INVALID, "decode_logits arguments");
   Arena& ws = c->ws;

@@ -82,6 +82,8 @@ struct OmniModel {
 };
 
 void omni_load(Ctx* c, int kind, const std::map<std::string, HostTensor>& t);
+// a second execution context over the same device weights: weight pointers copied, per-batch state fresh
+OmniModel* omni_share(const OmniModel* owner);
 void omni_encode(Ctx* c, const float* img_dev, const uint8_t* mask_dev, int B, int H, int W);
 void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_inst,
                  int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);

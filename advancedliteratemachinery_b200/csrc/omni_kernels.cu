@@ -659,10 +659,10 @@ void sine_pos(Ctx* c, const uint8_t* mask, int B, int H, int W, int h, int w, co
               uint8_t* kpm, float* scratch /* 2*B*h*w floats */) {
   const size_t sm = static_cast<size_t>(2) * h * w * sizeof(float);
   ALM_REQUIRE(sm <= 200 * 1024, ALM_ERR_UNSUPPORTED, "sine_pos: memory grid too large for shared memory");
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(sine_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    attr.mark();
   }
   const long npix = static_cast<long>(B) * h * w;
   float* yemb = scratch;
@@ -717,11 +717,11 @@ void cross_attn_q1(Ctx* c, const float* q, const bf16* kc_hi, const bf16* kc_lo,
   kps = (kps + 7) & ~7;
   const size_t sm = static_cast<size_t>(kps) * sizeof(float);
   ALM_REQUIRE(sm <= 160 * 1024, ALM_ERR_UNSUPPORTED, "cross_attn_q1: split too long for shared memory");
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     pin_carveout(cross_attn_q1_kernel);
-    attr = true;
+    attr.mark();
   }
   dim3 grid(nimg * 8, nsplit);
   cross_attn_q1_kernel<<<grid, XQ_THREADS, sm, c->stream>>>(q, kc_hi, kc_lo, vt_hi, vt_lo, kpm, M, Mpad, kps, partial,

@@ -370,8 +370,8 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
                    float* out_f32) {
   if (c->skipped(1)) return;
   const int nqb = (Ncap + 63) / 64;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     auto prep = [](auto* k) {
       ALM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, MQ_SMEM));
       pin_carveout(k);
@@ -379,7 +379,7 @@ void cross_attn_mq(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f3
     prep(cross_attn_mq_kernel<3, 0>); prep(cross_attn_mq_kernel<1, 0>);
     prep(cross_attn_mq_kernel<3, 1>); prep(cross_attn_mq_kernel<1, 1>);
     prep(cross_attn_mq_kernel<3, 2>); prep(cross_attn_mq_kernel<1, 2>);
-    attr = true;
+    attr.mark();
   }
   ALM_REQUIRE(q_f32 || q_hi, ALM_ERR_INVALID, "cross_attn_mq: no query operand");
   const bool q16 = Ncap <= 16;

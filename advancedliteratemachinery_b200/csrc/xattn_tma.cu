@@ -386,15 +386,15 @@ void cross_attn_tma(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f
                     int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo, float* out_f32) {
   if (c->skipped(1)) return;
   const int nqb = (Ncap + 63) / 64;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     auto prep = [](auto* k) {
       ALM_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM));
       pin_carveout(k);
     };
     prep(cross_attn_tma_kernel<3, 1>); prep(cross_attn_tma_kernel<1, 1>);
     prep(cross_attn_tma_kernel<3, 2>); prep(cross_attn_tma_kernel<1, 2>);
-    attr = true;
+    attr.mark();
   }
   ALM_REQUIRE(q_f32 || q_hi, ALM_ERR_INVALID, "cross_attn_tma: no query operand");
   const bool q16 = Ncap <= 16;

@@ -60,7 +60,8 @@ typedef struct alm_ctx alm_ctx;
 
 /* One state-dict entry.  `name` is the reference key verbatim
  * (e.g. "backbone.0.layers.2.blocks.5.attn.qkv.weight", "module.mgp_str.blocks.0.norm1.bias").
- * `data` is a HOST pointer; the library converts and uploads, the caller keeps ownership. */
+ * `data` is a HOST pointer (or NULL: shape-only placeholder, see alm_load_weights); the library converts and uploads,
+ * the caller keeps ownership. */
 typedef struct alm_tensor_desc {
   const char* name;
   const void* data;
@@ -123,6 +124,39 @@ ALM_API int alm_bench_gemm_ex(alm_ctx* ctx, int M, int N, int K, int batch, int 
 /* Replaces reference `model.load_state_dict(torch.load(path)['model'])`
  * (OCR/OmniParser/utils/checkpointer.py:44-47; OCR/MGP-STR/test_final.py:353-356). */
 ALM_API int alm_load_weights(alm_ctx* ctx, int model_kind, const alm_tensor_desc* tensors, int n);
+/* A descriptor with data == NULL is a shape-only placeholder: the tensor is laid out (zeros) exactly as if it had been
+ * loaded, and its values arrive later through alm_broadcast_weights -- what the non-root ranks of a multi-GPU job do. */
+
+/* One model, many execution contexts: `ctx` (same device as `owner`) serves the weights already resident in `owner`
+ * -- no copy, the device slabs are reference-counted and freed with the last context using them.  Per-batch state
+ * (arena, K/V caches, captured graphs, stream) stays private to each context, so contexts can run concurrently from
+ * different host threads.  Replaces the reference's one-module-per-process shape (OCR/OmniParser/model/__init__.py:7-19)
+ * for serving several batches in flight per GPU. */
+ALM_API int alm_share_weights(alm_ctx* ctx, alm_ctx* owner);
+
+/* Stream ordering for device-resident inputs / outputs.  The context enqueues on its own stream (alm_init), which is
+ * NOT ordered with the caller's streams: before passing device buffers written on `producer_stream` call
+ * alm_stream_wait (the context's stream waits for everything enqueued on producer_stream so far); before reading
+ * device outputs (alm_pre_*) on `consumer_stream` call alm_stream_release.  Host buffers need neither. */
+ALM_API int alm_stream_wait(alm_ctx* ctx, void* producer_stream /* cudaStream_t */);
+ALM_API int alm_stream_release(alm_ctx* ctx, void* consumer_stream /* cudaStream_t */);
+
+/* ---- multi-GPU: pages shard across GPUs with no data-path collective ------- */
+/* The reference has no inference collective (its NCCL use is DDP training, OCR/OmniParser/utils/dist.py:25,43-44);
+ * a data-parallel serving job needs two: ONE broadcast of the weights at start-up and ONE gather of the decoded
+ * sequences per batch.  NCCL is bound at run time (dlopen libnccl.so.2); ALM_ERR_UNSUPPORTED if it is absent.
+ *   rank 0: alm_comm_unique_id(id) -> ship the 128 bytes to the other ranks by any means (file, socket, MPI, ...)
+ *   all   : alm_comm_init(ctx, id, rank, world)        (or alm_comm_attach with a communicator the caller owns)
+ *   all   : alm_load_weights (root: real tensors; others: shape-only placeholders), then alm_broadcast_weights(ctx, 0):
+ *           the converted bf16 hi/lo planes and fp32 vectors travel once over NVLink straight into place
+ *   batch : alm_gather_sequences(ctx, buf, bytes, recv): all-gather of one fixed-size packed buffer per rank
+ *           (send: host or device; recv: host, world * bytes, rank-major, or NULL), on the context's stream.
+ * With world == 1 (no communicator) broadcast is a no-op and gather a copy. */
+ALM_API int alm_comm_unique_id(void* id128);
+ALM_API int alm_comm_init(alm_ctx* ctx, const void* id128, int rank, int world);
+ALM_API int alm_comm_attach(alm_ctx* ctx, void* nccl_comm /* ncclComm_t, caller-owned */, int rank, int world);
+ALM_API int alm_broadcast_weights(alm_ctx* ctx, int root);
+ALM_API int alm_gather_sequences(alm_ctx* ctx, const void* send, size_t bytes_per_rank, void* recv_host);
 
 /* ---- OmniParser ---------------------------------------------------------------------------- */
 /* Vocabulary / decode configuration: OCR/OmniParser/utils/parser.py:16-21,91-103. */

@@ -338,6 +338,75 @@ def greedy_text_spotting(memory, mem_kpm, pos, sd, pt_prompt, pt_seq_length, rec
     return (res, logs) if return_logits else res
 
 
+def greedy_min_gaps(logs):
+    """Smallest top-1 / top-2 LOGIT gap among the candidates each greedy step may pick (pt: bins, + pt_eos on even
+    steps; poly: bins; rec: chars, pad and rec_eos -- transformer.py:110-123,257-259,274-278) for the per-step logits
+    returned by ``greedy_text_spotting(..., return_logits=True)``.  A fixture whose gaps are all far above the CUDA
+    path's logit error (~1e-5) admits no near-tie excuse: its ids must match bit for bit."""
+    nb = W.NUM_BINS
+    out = {}
+    for kind, steps in logs.items():
+        g = float('inf')
+        for i, lg in enumerate(steps):
+            a = torch.zeros(lg.shape[-1], dtype=torch.bool)
+            if kind == 'pt':
+                a[:nb] = True
+                if i % 2 == 0:
+                    a[W.PT_EOS] = True
+            elif kind == 'poly':
+                a[:nb] = True
+            else:
+                a[nb:W.PT_EOS] = True
+                a[W.REC_EOS] = True
+            top = lg.masked_fill(~a, float('-inf')).topk(2, dim=-1).values
+            g = min(g, float((top[:, 0] - top[:, 1]).min()))
+        out[kind] = g
+    return out
+
+
+def step_candidates(kind, step, V):
+    """Ids a greedy step may emit (transformer.py:110-123,257-259,274-278); text spotting."""
+    a = torch.zeros(V, dtype=torch.bool)
+    nb = W.NUM_BINS
+    if kind == 'pt':
+        a[:nb] = True
+        if step % 2 == 0:
+            a[W.PT_EOS] = True
+    elif kind == 'poly':
+        a[:nb] = True
+    else:
+        a[nb:W.PT_EOS] = True
+        a[W.REC_EOS] = True
+    return a
+
+
+def teacher_forced_gaps(memory, mem_kpm, pos, sd, pt_prompt, pt, poly, rec):
+    """One teacher-forced pass per loop over given greedy outputs (pt [1,2N], poly [1,32N], rec [1,N,L]): for every
+    generated token the top-1 / top-2 gap among the step's candidates, and whether the restatement's argmax equals the
+    given id everywhere.  Because prefix states are invariant under the causal mask this reproduces the
+    no-cache greedy loops step for step.  Returns {kind: (gaps [n_seq, steps], all_equal)}."""
+    n = pt.numel() // 2
+    n_prompt = pt_prompt.shape[1]
+    full = {'pt': torch.cat([pt_prompt, pt.reshape(1, -1)], 1),
+            'poly': torch.cat([pt.reshape(-1, 2), torch.full((n, 1), W.POLY_SOS, dtype=torch.long), poly.reshape(n, -1)], 1),
+            'rec': torch.cat([pt.reshape(-1, 2), torch.full((n, 1), W.REC_SOS, dtype=torch.long), rec.reshape(n, -1)], 1)}
+    start = {'pt': n_prompt, 'poly': 3, 'rec': 3}
+    out = {}
+    for kind, seq in full.items():
+        lg = decode_logits(seq, memory, mem_kpm, pos, sd, kind)
+        s0 = start[kind]
+        steps = seq.shape[1] - s0
+        gaps = torch.zeros(seq.shape[0], steps)
+        ok = True
+        for t in range(steps):
+            a = step_candidates(kind, t, lg.shape[-1])
+            top = lg[:, s0 - 1 + t].masked_fill(~a, float('-inf')).topk(2, dim=-1)
+            gaps[:, t] = top.values[:, 0] - top.values[:, 1]
+            ok = ok and bool((top.indices[:, 0] == seq[:, s0 + t]).all())
+        out[kind] = (gaps, ok)
+    return out
+
+
 def greedy_kie(memory, mem_kpm, pos, sd, pt_prompt, pt_seq_length, rec_length, vie, image_size, classes):
     """KIE eval branch for ONE image: decode_pt_seq with infer_vie (transformer.py:102-141, :117-123) followed by
     decode_vie_pt_poly_rec_seq (:143-217).  Returns None when no token is produced, else the reference's

@@ -432,8 +432,6 @@ def test_fused_cross_attention_8warp_variant_matches():
             assert _maxrel(alt, ref) < 2e-5, (image, n, _maxrel(alt, ref))
 
 
-@pytest.mark.skipif(os.environ.get('ALM_RUN_UNVALIDATED') != '1',
-                    reason='added after the round-1 GPU budget was spent (set ALM_RUN_UNVALIDATED=1)')
 def test_more_than_32_pages_leave_the_skinny_path_and_stay_batch_invariant():
     """34 pages per call: the pt loop has more than 32 live sequences, so its linears run on the tensor-core GEMM
     path and the 16-row fused cross-attention takes fp32 queries / writes split outputs.  Every page must decode to
@@ -455,8 +453,6 @@ def test_more_than_32_pages_leave_the_skinny_path_and_stay_batch_invariant():
                     assert torch.equal(x, y)
 
 
-@pytest.mark.skipif(os.environ.get('ALM_RUN_UNVALIDATED') != '1',
-                    reason='xattn_impl 2 (TMA + mbarrier pipeline) was written after the round-1 GPU budget was spent')
 def test_tma_cross_attention_variant_matches_the_default_kernel():
     """`xattn_impl` 2 (csrc/xattn_tma.cu) against the default fused kernel: 70 / 33 sequences (8 math warps), 10 and 1
     (the 16-row pt variant), ragged key range, masked keys, two images, then a whole greedy decode."""
@@ -494,8 +490,6 @@ def test_tma_cross_attention_variant_matches_the_default_kernel():
         m.ctx.set_option('xattn_impl', 0)
 
 
-@pytest.mark.skipif(os.environ.get('ALM_RUN_UNVALIDATED') != '1',
-                    reason='added after the round-1 GPU budget was spent (set ALM_RUN_UNVALIDATED=1)')
 def test_config5_geometry_largest_page_and_long_point_sequence():
     """BASELINE config-5 geometry: one 1920 x 1920 page (M = 120 x 120 = 14 400 memory tokens, 225 key blocks per
     (image, head)) through the encoder against the CPU oracle, then a long point sequence (the `table` use: many

@@ -9,10 +9,6 @@ import torch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
-# The CUDA pre-processing kernels were written after round 1's GPU budget was spent: they compile for sm_100a and the
-# arithmetic they implement is pinned on the CPU, but they have not run on a B200 yet.  Opt in with ALM_RUN_UNVALIDATED=1.
-unvalidated = pytest.mark.skipif(os.environ.get('ALM_RUN_UNVALIDATED') != '1',
-                                 reason='CUDA pre-processing not yet validated on a B200 (set ALM_RUN_UNVALIDATED=1)')
 
 
 def _omni():
@@ -130,7 +126,6 @@ def test_size_plan_equals_reference_rule():
 
 
 @pytest.mark.gpu
-@unvalidated
 @pytest.mark.parametrize('on_device', [False, True])
 def test_gpu_omni_pages_equal_reference(on_device):
     from advancedliteratemachinery_b200 import _lib, preprocess as P
@@ -144,7 +139,6 @@ def test_gpu_omni_pages_equal_reference(on_device):
 
 
 @pytest.mark.gpu
-@unvalidated
 def test_gpu_mgp_crops_equal_reference():
     from advancedliteratemachinery_b200 import _lib, preprocess as P
     z, crops = _mgp()
@@ -155,7 +149,6 @@ def test_gpu_mgp_crops_equal_reference():
 
 
 @pytest.mark.gpu
-@unvalidated
 def test_gpu_page_scale_resize_matches_oracle():
     """A real page size (1500 x 1100 -> shorter side 1024): bit-exact against the oracle."""
     from advancedliteratemachinery_b200 import _lib, preprocess as P
