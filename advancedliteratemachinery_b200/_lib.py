@@ -68,11 +68,15 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     'alm_omni_decode_kie': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'alm_omni_decode_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     'alm_omni_decode_logits': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'alm_omni_vocab': (C.c_int, [C.c_void_p]),
     'alm_omni_last_timing': (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'alm_mgpstr_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    'alm_mgpstr_info': (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.c_void_p]),
     'alm_op_linear': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int]),
     'alm_op_layernorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_long,
@@ -131,6 +135,7 @@ class Context:
             raise AlmError(rc, 'alm_init failed (no sm_100a CUDA device? this library has no fallback path)')
         self.h = h
         self.device = device
+        self.comm_rank, self.comm_world = 0, 1
 
     def check(self, rc):
         if rc != ALM_OK:
@@ -202,6 +207,72 @@ class Context:
             for j, s in enumerate(t.shape):
                 descs[i].shape[j] = s
         self.check(self.lib.alm_load_weights(self.h, kind, descs, len(state_dict)))
+
+    def load_placeholders(self, kind: int, meta):
+        """Shape-only load (data == NULL) of [(name, shape, dtype_code), ...]: lays the weights out exactly like
+        `load_state_dict` would; the values arrive through `broadcast_weights` (non-root ranks of a multi-GPU job)."""
+        descs = (TensorDesc * len(meta))()
+        for i, (k, shape, dt) in enumerate(meta):
+            assert len(shape) <= 4, k
+            descs[i].name = k.encode()
+            descs[i].data = None
+            descs[i].dtype = dt
+            descs[i].ndim = len(shape)
+            for j, s in enumerate(shape):
+                descs[i].shape[j] = s
+        self.check(self.lib.alm_load_weights(self.h, kind, descs, len(meta)))
+
+    @staticmethod
+    def state_dict_meta(state_dict):
+        """[(name, shape, dtype_code)] of a reference state dict, as `load_placeholders` takes it."""
+        import torch
+        code = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16, torch.int64: DT_I64}
+        return [(k, tuple(v.shape), code.get(v.dtype, DT_F32)) for k, v in state_dict.items()]
+
+    def share_weights(self, owner: 'Context'):
+        """Serve the weights resident in `owner` (same GPU) from this context too: no copy (alm_share_weights)."""
+        self.check(self.lib.alm_share_weights(self.h, owner.h))
+        self._weights_owner = owner  # keeps the Python object alive; the device slabs are ref-counted in the library
+
+    def wait_stream(self, cuda_stream: int):
+        """The context's stream waits for everything enqueued so far on `cuda_stream` (device inputs written there)."""
+        self.check(self.lib.alm_stream_wait(self.h, C.c_void_p(cuda_stream)))
+
+    def release_stream(self, cuda_stream: int):
+        """`cuda_stream` waits for everything this context has enqueued so far (device outputs read there)."""
+        self.check(self.lib.alm_stream_release(self.h, C.c_void_p(cuda_stream)))
+
+    def wait_torch(self, *tensors):
+        """Order the context's stream after torch's current stream when any argument is a CUDA tensor."""
+        import torch
+        for t in tensors:
+            if t is not None and t.is_cuda:
+                self.wait_stream(torch.cuda.current_stream(t.device).cuda_stream)
+                return
+
+    # ---- multi-GPU (alm_comm_*): one weight broadcast, one gather per batch
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.alm_comm_unique_id(buf)
+        if rc != ALM_OK:
+            raise AlmError(rc, 'alm_comm_unique_id failed (NCCL not loadable?)')
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        assert len(uid) == 128
+        self.check(self.lib.alm_comm_init(self.h, C.create_string_buffer(uid, 128), int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def broadcast_weights(self, root: int = 0):
+        self.check(self.lib.alm_broadcast_weights(self.h, int(root)))
+
+    def gather(self, send, world: int):
+        """All-gather of one equal-size buffer per rank (numpy array in, [world, ...] numpy array out)."""
+        import numpy as np
+        send = np.ascontiguousarray(send)
+        recv = np.empty((world,) + send.shape, dtype=send.dtype)
+        self.check(self.lib.alm_gather_sequences(self.h, send.ctypes.data, send.nbytes, recv.ctypes.data))
+        return recv
 
     def close(self):
         if getattr(self, 'h', None):

@@ -639,6 +639,14 @@ int alm_omni_decode_kie(alm_ctx* h, const int64_t* pt_prompt, int n_prompt, cons
   });
 }
 
+int alm_omni_decode_points(alm_ctx* h, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_tok,
+                           int64_t* pt_tokens, float* pt_probs) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(pt_prompt && cfg && n_tok && pt_tokens, ALM_ERR_INVALID, "null argument");
+    omni_decode_points(&h->c, pt_prompt, n_prompt, *cfg, n_tok, pt_tokens, pt_probs);
+  });
+}
+
 int alm_omni_decode_logits(alm_ctx* h, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits) {
   return guarded(h, [&] {
     ALM_REQUIRE(seq && logits, ALM_ERR_INVALID, "null argument");
@@ -654,6 +662,13 @@ int alm_mgpstr_forward(alm_ctx* h, const float* img, int B, float* attn, float* 
     const float* dimg = static_cast<const float*>(
         stage_input(h, img, static_cast<size_t>(B) * 3 * 32 * 128 * sizeof(float), &h->dev_in, &h->dev_in_bytes));
     mgp_forward(&h->c, dimg, B, attn, char_logits, bpe_logits, wp_logits, ids, prob);
+  });
+}
+
+int alm_mgpstr_info(alm_ctx* h, int* dim, int* depth, int* heads, int* n_a3, int* vocab3) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(h->c.mgp != nullptr, ALM_ERR_STATE, "alm_mgpstr_info before alm_load_weights");
+    mgp_info(h->c.mgp, dim, depth, heads, n_a3, vocab3);
   });
 }
 

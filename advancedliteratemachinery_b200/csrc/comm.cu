@@ -115,7 +115,7 @@ void comm_release(Ctx* c) {
 // and shapes (placeholders on the non-root ranks), so the bump-allocated layout is identical; checked by size.
 void comm_broadcast_weights(Ctx* c, int root) {
   ALM_REQUIRE(c->wstore && !c->wstore->slabs.empty(), ALM_ERR_STATE, "alm_broadcast_weights before alm_load_weights");
-  if (c->comm_world == 1) return;
+  if (c->comm == nullptr && c->comm_world == 1) return;  // single-GPU job without a communicator: nothing to do
   ALM_REQUIRE(c->comm != nullptr, ALM_ERR_STATE, "alm_broadcast_weights without a communicator (alm_comm_init)");
   ALM_REQUIRE(root >= 0 && root < c->comm_world, ALM_ERR_INVALID, "broadcast root");
   ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
@@ -140,7 +140,6 @@ void comm_broadcast_weights(Ctx* c, int root) {
     ALM_CHECK_NCCL(nccl().Broadcast(c->wstore->slabs[i], c->wstore->slabs[i], used[i], ncclUint8, root, comm, c->stream));
   ALM_CHECK_NCCL(nccl().GroupEnd());
   ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += 1;
 }
 
 // All-gather of one fixed-size buffer per rank (the decoded sequences of a batch: int32 ids + fp32 probabilities packed
@@ -149,7 +148,7 @@ void comm_broadcast_weights(Ctx* c, int root) {
 void comm_gather(Ctx* c, const void* send, size_t bytes, void* recv_host) {
   ALM_REQUIRE(send && bytes > 0, ALM_ERR_INVALID, "alm_gather_sequences arguments");
   const int world = c->comm_world;
-  if (world == 1) {
+  if (world == 1 && c->comm == nullptr) {
     if (recv_host) {
       cudaPointerAttributes a;
       const bool dev = cudaPointerGetAttributes(&a, send) == cudaSuccess && a.type == cudaMemoryTypeDevice;
@@ -177,7 +176,6 @@ void comm_gather(Ctx* c, const void* send, size_t bytes, void* recv_host) {
   ALM_CHECK_NCCL(nccl().AllGather(dsend, drecv, bytes, ncclUint8, static_cast<ncclComm_t>(c->comm), c->stream));
   if (recv_host) ALM_CHECK_CUDA(cudaMemcpyAsync(recv_host, drecv, bytes * world, cudaMemcpyDeviceToHost, c->stream));
   ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += 1;
 }
 
 }  // namespace alm

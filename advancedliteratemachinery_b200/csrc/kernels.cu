@@ -33,9 +33,10 @@ __device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, long off, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather + LayerNorm + split.  One warp per output row; lane holds NV float4 (C = 128*NV).
+// gather + LayerNorm + split.  One warp per output row; lane holds NV float4 (C = 128*NV, or CW < 128*NV with the
+// tail lanes of the last float4 idle: CW = 192 is the ViT-tiny width of MGP-STR, mgp_str.py:207-216).
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, int CW = NV * 128>
 __global__ void __launch_bounds__(256)
 gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict__ map, int nsrc, int Cs, long rows,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int zero_missing,
@@ -45,19 +46,20 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
   const long r = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
-  constexpr int C = NV * 128;
+  constexpr int C = CW;
+  constexpr bool kFull = (CW == NV * 128);
   float4 v[NV];
   bool any = false;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int e = 4 * (lane + 32 * j);
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kFull && e >= C) continue;
     const int s = e / Cs;
     const long sr = map ? map[r * nsrc + s] : r * nsrc + s;
     if (sr >= 0) {
       v[j] = *reinterpret_cast<const float4*>(src + sr * lds + (e - s * Cs));
       any = true;
-    } else {
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   const bool dead = zero_missing && !__any_sync(0xffffffffu, any);
@@ -69,6 +71,7 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
     float q = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
+      if (!kFull && 4 * (lane + 32 * j) >= C) continue;
       const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
@@ -76,6 +79,7 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int e = 4 * (lane + 32 * j);
+      if (!kFull && e >= C) continue;
       const float4 g = *reinterpret_cast<const float4*>(gamma + e);
       const float4 b = *reinterpret_cast<const float4*>(beta + e);
       v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
@@ -87,6 +91,7 @@ gather_ln_kernel(const float* __restrict__ src, long lds, const int* __restrict_
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int e = 4 * (lane + 32 * j);
+    if (!kFull && e >= C) continue;
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ldo_f32 + e) = v[j];
     if (out_hi) store_split4(out_hi, out_lo, r * ldo_bf + e, v[j]);
     if (out2_hi || out2_f32) {
@@ -550,8 +555,9 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
   if (c->skipped(4)) return;
   if (rows == 0) return;
   const int C = nsrc * Cs;
-  ALM_REQUIRE(C % 128 == 0 && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID, "gather_ln: width must be a multiple of 128");
-  const int nv = C / 128;
+  ALM_REQUIRE((C % 128 == 0 || C == 192) && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID,
+              "gather_ln: width must be a multiple of 128 (or 192)");
+  const int nv = C == 192 ? 192 : C / 128;
   const int wpb = 8;
   dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb)), block(wpb * 32);
 #define ALM_GLN(NVV)                                                                                              \
@@ -563,6 +569,13 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
     break;
   switch (nv) {
     ALM_GLN(1) ALM_GLN(2) ALM_GLN(3) ALM_GLN(4) ALM_GLN(6) ALM_GLN(8) ALM_GLN(16)
+    case 192: {
+      auto k192 = gather_ln_kernel<2, 192>;
+      ALM_PIN_CARVEOUT(k192);
+      k192<<<grid, block, 0, c->stream>>>(src, lds, map, nsrc, Cs, rows, gamma, beta, eps, zero_missing ? 1 : 0, add,
+                                          ld_add, out_f32, ldo_f32, out_hi, out_lo, ldo_bf, out2_hi, out2_lo, out2_f32);
+      break;
+    }
     default:
       throw AlmError{ALM_ERR_UNSUPPORTED, "gather_ln: unsupported width " + std::to_string(C)};
   }

@@ -41,9 +41,18 @@ struct MgpModel {
   float* pos = nullptr;   // [257, D]
   std::vector<MgpBlock> blocks;
   MgpA3 a3[3];
+  int n_a3 = 3;  // 3 = MGP-STR (char, bpe, wp); 1 = the char-only CHAR-STR ablation (modules/char_str.py:43-81)
 };
 
 void mgp_free(MgpModel* m) { delete m; }
+void mgp_info(const MgpModel* m, int* dim, int* depth, int* heads, int* n_a3, int* vocab3) {
+  if (dim) *dim = m->D;
+  if (depth) *depth = m->depth;
+  if (heads) *heads = m->heads;
+  if (n_a3) *n_a3 = m->n_a3;
+  if (vocab3)
+    for (int a = 0; a < 3; ++a) vocab3[a] = a < m->n_a3 ? m->a3[a].V : 0;
+}
 MgpModel* mgp_share(const MgpModel* owner) { return new MgpModel(*owner); }
 
 namespace {
@@ -156,7 +165,9 @@ void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& tin) {
   ALM_REQUIRE(pe.shape.size() == 3 && pe.shape[1] == T, ALM_ERR_INVALID, "pos_embed must be [1,257,D] (32x128 input, patch 4)");
   m->D = static_cast<int>(pe.shape[2]);
   const int D = m->D;
-  ALM_REQUIRE(D % 128 == 0 && D % 64 == 0, ALM_ERR_UNSUPPORTED, "embed dim must be a multiple of 128 (base=768, large=1024)");
+  // tiny 192 / small 384 / base 768 / large 1024 (mgp_str.py:176-230); every variant has 64-wide heads
+  ALM_REQUIRE(D % 64 == 0 && (D % 128 == 0 || D == 192), ALM_ERR_UNSUPPORTED,
+              "embed dim must be 192 or a multiple of 128 (tiny=192, small=384, base=768, large=1024)");
   m->heads = D / 64;
   ALM_REQUIRE((D / 8) % 8 == 0, ALM_ERR_UNSUPPORTED, "A^3 group width must be a multiple of 8");
   m->depth = 0;
@@ -184,7 +195,10 @@ void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& tin) {
     w.fc2 = ld_lin(c, t, p + "mlp.fc2", D, 4 * D);
   }
   const char* names[3] = {"char", "bpe", "wp"};
-  for (int a = 0; a < 3; ++a) {
+  // CHAR-STR (modules/char_str.py:43-81): only the character A^3 module, and its logits come from timm's own
+  // classifier `head` (char_str.py:70 calls self.head, not the char_head that reset_classifier creates)
+  m->n_a3 = t.count("bpe_tokenLearner.token_norm.weight") ? 3 : 1;
+  for (int a = 0; a < m->n_a3; ++a) {
     const std::string p = std::string(names[a]) + "_tokenLearner.";
     MgpA3& w = m->a3[a];
     w.token_norm = ld_ln(c, t, p + "token_norm", D);
@@ -197,11 +211,12 @@ void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& tin) {
     w.w0 = upload_split(c, w0.f32.data(), D, D / 8, 0);
     w.w1 = upload_split(c, w1.f32.data(), NTOK, D, 0);
     w.feat = upload_split(c, wf.f32.data(), D, D / 8, 0);
-    const HostTensor& hw = need(t, std::string(names[a]) + "_head.weight");
+    const std::string hname = m->n_a3 == 1 ? std::string("head") : std::string(names[a]) + "_head";
+    const HostTensor& hw = need(t, hname + ".weight");
     ALM_REQUIRE(hw.shape.size() == 2 && hw.shape[1] == D, ALM_ERR_INVALID, "head shape mismatch");
     w.V = static_cast<int>(hw.shape[0]);
     w.Vpad = (w.V + 7) & ~7;
-    w.head = ld_lin(c, t, std::string(names[a]) + "_head", w.V, D);
+    w.head = ld_lin(c, t, hname, w.V, D);
   }
   mgp_free(c->mgp);
   c->mgp = m;
@@ -286,7 +301,7 @@ void mgp_forward(Ctx* c, const float* img, int B, float* attn_out, float* char_l
   const size_t a3_mark = ws.mark();
   float* logit_dst[3] = {char_logits, bpe_logits, wp_logits};
   const int G = 8, Dg = D / 8;
-  for (int a = 0; a < 3; ++a) {
+  for (int a = 0; a < m->n_a3; ++a) {
     ws.release(a3_mark);
     const MgpA3& w = m->a3[a];
     SB tn = sb(c, R * D);

@@ -709,7 +709,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
 // tokens form (x, y) instances and in the number of logits entering the poly / rec softmax.
 void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, bool kie,
                       int32_t* n_tok_out, int64_t* pt_tok_out, float* pt_prob_out, int32_t* n_inst, int32_t* inst_pos,
-                      int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob) {
+                      int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob, bool points_only = false) {
   OmniModel* m = c->omni;
   ALM_REQUIRE(m && m->encoded, ALM_ERR_STATE, "alm_omni_decode before alm_omni_encode");
   ALM_REQUIRE(c->xattn_impl != 1 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
@@ -723,8 +723,8 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   const bool pt_clamped = pt_steps < cfg.pt_seq_length;
   ALM_REQUIRE(cfg.vie_categories == m->vie, ALM_ERR_INVALID, "vie_categories does not match the loaded checkpoint");
   ALM_REQUIRE(kie == (m->vie > 0), ALM_ERR_INVALID, "use alm_omni_decode for text spotting and alm_omni_decode_kie for KIE");
-  ALM_REQUIRE(cfg.max_instances >= (pt_steps / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
-  ALM_REQUIRE(cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
+  ALM_REQUIRE(points_only || cfg.max_instances >= (pt_steps / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
+  ALM_REQUIRE(points_only || cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
   const int B = m->B;
   Arena& ws = c->ws;
   ws.release(m->ws_mark);
@@ -817,6 +817,14 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
     int len = h_ntok[b];
     if (len % 2) --len;  // transformer.py:138-139 (applied in both modes by the reference)
     const int* t = &h_tok[static_cast<size_t>(b) * Tpt + n_prompt];
+    if (points_only) {  // the raw point sequence is the result (decode_pt_seq alone, transformer.py:102-141)
+      n_tok_out[b] = len;
+      for (int i = 0; i < len; ++i) {
+        pt_tok_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = t[i];
+        if (pt_prob_out) pt_prob_out[static_cast<size_t>(b) * cfg.pt_seq_length + i] = h_prob[static_cast<size_t>(b) * pt_steps + i];
+      }
+      continue;
+    }
     if (!kie) {
       for (int i = 0; i + 1 < len; i += 2) starts[b].push_back(i);
     } else {
@@ -840,6 +848,12 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
         pt[(static_cast<size_t>(b) * maxI + n) * 2 + 1] = t[starts[b][n] + 1];
       }
     }
+  }
+  if (points_only) {
+    c->timing_valid[1] = true;
+    ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[4], c->stream));
+    ws.release(m->ws_mark);
+    return;
   }
   if (Ncap == 0) return;
 
@@ -933,6 +947,12 @@ void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_d
                      int64_t* rec, float* rec_prob) {
   omni_decode_impl(c, pt_prompt, n_prompt, cfg, true, n_tok, pt_tokens, pt_probs, n_inst, inst_pos, nullptr, poly, rec,
                    rec_prob);
+}
+
+void omni_decode_points(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_tok,
+                        int64_t* pt_tokens, float* pt_probs) {
+  omni_decode_impl(c, pt_prompt, n_prompt, cfg, c->omni && c->omni->vie > 0, n_tok, pt_tokens, pt_probs, nullptr, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, true);
 }
 
 // Teacher-forced logits for one image: every position of every sequence (Transformer.decode, :74-100).

@@ -90,6 +90,8 @@ void omni_decode(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decod
 void omni_decode_kie(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_tok,
                      int64_t* pt_tokens, float* pt_probs, int32_t* n_inst, int32_t* inst_pos, int64_t* poly,
                      int64_t* rec, float* rec_prob);
+void omni_decode_points(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg& cfg, int32_t* n_tok,
+                        int64_t* pt_tokens, float* pt_probs);
 void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_seq, int len, float* logits);
 
 // kernels (omni_kernels.cu)

@@ -1,14 +1,18 @@
-"""Data-parallel plumbing over torch.distributed (NCCL on the GPU box, gloo in the CPU tests).
+"""Data-parallel plumbing.  The path shards by page: every rank encodes / decodes its own
+pages with replicated weights, so there are exactly two collectives -- ONE broadcast of the weights at start-up and ONE
+gather of fixed-stride int32 sequence buffers per batch -- and none on the data path.
 
-The path shards by page: every rank encodes/decodes its own pages with replicated weights, so there are
-exactly two collectives: ONE broadcast of the packed weights at start-up and ONE gather
-of fixed-stride int32 sequence buffers per batch.  No collective on the data path.
-"""
+On the GPU both run inside libalm_ocr.so over its own NCCL communicator (`alm_comm_init`, `alm_broadcast_weights`,
+`alm_gather_sequences`): the converted bf16 planes land in place on every rank, and a C++ host can do the same
+without Python.  torch.distributed is only the rendezvous that ships the 128-byte NCCL id and the tensor shapes.  The
+packing, padding and page re-ordering logic is transport-independent and is exercised on CPU with gloo
+(tests/test_dist_cpu.py)."""
 from __future__ import annotations
 
 from collections import OrderedDict
 from typing import List, Optional
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -18,8 +22,37 @@ def shard_pages(n_pages: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_pages, world))
 
 
+def pages_per_rank(n_pages: int, world: int) -> int:
+    return (n_pages + world - 1) // world
+
+
+# ------------------------------------------------------------------------------------------------ weights
+def init_comm(ctx, device: Optional[torch.device] = None):
+    """Create the library's NCCL communicator for `ctx`: rank 0 makes the id, torch.distributed ships its 128 bytes."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, device=device)
+    ctx.comm_init(box[0], rank, world)
+
+
+def load_weights_broadcast(ctx, kind: int, state_dict: Optional[dict], src: int = 0,
+                           device: Optional[torch.device] = None):
+    """The weight start-up of a multi-GPU job: `src` converts the checkpoint (alm_load_weights), every other rank lays
+    out placeholders of the same shapes, then ONE NCCL broadcast of the device slabs (bf16 hi/lo planes + fp32 vectors)
+    puts the weights in place.  Needs `init_comm(ctx)` first.  Only names / shapes travel through torch.distributed."""
+    rank = dist.get_rank()
+    meta = [ctx.state_dict_meta(state_dict) if rank == src else None]
+    dist.broadcast_object_list(meta, src=src, device=device)
+    if rank == src:
+        ctx.load_state_dict(kind, state_dict)
+    else:
+        ctx.load_placeholders(kind, meta[0])
+    ctx.broadcast_weights(src)
+
+
 def broadcast_state_dict(sd: Optional[dict], src: int = 0, device: Optional[torch.device] = None) -> OrderedDict:
-    """One metadata broadcast (names/shapes, a few KB) + ONE flat fp32 broadcast of every tensor."""
+    """Host-level alternative (any torch.distributed backend): one metadata broadcast + ONE flat fp32 broadcast of every
+    tensor, returning the state dict on every rank.  The GPU job uses `load_weights_broadcast` instead."""
     rank = dist.get_rank()
     meta = [None]
     if rank == src:
@@ -43,20 +76,22 @@ def broadcast_state_dict(sd: Optional[dict], src: int = 0, device: Optional[torc
     return out
 
 
-def pack_sequences(outs, vocab, max_inst: int) -> torch.Tensor:
-    """Per-rank decode results -> int32 [B, 1 + max_inst * (2 + 32 + L)] (count first, then pt|poly|rec rows;
-    probabilities travel as their fp32 bit patterns in a second plane)."""
+# ------------------------------------------------------------------------------------------------ sequences
+def pack_sequences(outs, vocab, max_inst: int, rows: Optional[int] = None) -> torch.Tensor:
+    """Per-rank decode results -> int32 [rows, 2, 1 + max_inst * (2 + 32 + L)] (count first, then pt|poly|rec rows;
+    probabilities travel as their fp32 bit patterns in the second plane).  `rows` > len(outs) pads with empty pages so
+    that every rank ships the same size when the pages do not divide evenly."""
     L = vocab.rec_length
     stride = 2 + 32 + L
-    buf = torch.zeros(len(outs), 2, 1 + max_inst * stride, dtype=torch.int32)
+    buf = torch.zeros(max(rows or 0, len(outs)), 2, 1 + max_inst * stride, dtype=torch.int32)
     for b, o in enumerate(outs):
         if o is None:
             continue
         (pt, poly, rec), (probs,) = o
         n = pt.numel() // 2
         buf[b, 0, 0] = n
-        rows = torch.cat([pt.reshape(n, 2), poly.reshape(n, 32), rec.reshape(n, L)], dim=1).to(torch.int32)
-        buf[b, 0, 1:1 + n * stride] = rows.reshape(-1)
+        r = torch.cat([pt.reshape(n, 2), poly.reshape(n, 32), rec.reshape(n, L)], dim=1).to(torch.int32)
+        buf[b, 0, 1:1 + n * stride] = r.reshape(-1)
         pr = torch.zeros(n, stride, dtype=torch.float32)
         pr[:, 34:] = probs
         buf[b, 1, 1:1 + n * stride] = pr.view(torch.int32).reshape(-1)
@@ -78,20 +113,53 @@ def unpack_sequences(buf: torch.Tensor, vocab) -> list:
     return outs
 
 
-def gather_sequences(outs, vocab, dst: int = 0, device: Optional[torch.device] = None):
-    """ONE gather of the packed sequences to `dst`; returns the flat list of per-page results there
-    (rank-major: pages of rank 0, then rank 1, ...), None elsewhere."""
-    world, rank = dist.get_world_size(), dist.get_rank()
+def interleave_pages(per_rank: List[list], n_pages: int) -> list:
+    """per_rank[r][i] is global page r + i * world (round-robin sharding): back to page order, padding rows dropped."""
+    world = len(per_rank)
+    out = [None] * n_pages
+    for r, rows in enumerate(per_rank):
+        for i, o in enumerate(rows):
+            p = r + i * world
+            if p < n_pages:
+                out[p] = o
+    return out
+
+
+def gather_sequences(outs, vocab, n_pages: Optional[int] = None, ctx=None, dst: Optional[int] = None,
+                     device: Optional[torch.device] = None):
+    """ONE gather of the packed sequences of a batch.
+
+    `outs`: this rank's per-page results for its round-robin shard of `n_pages` global pages (default: every rank holds
+    len(outs) pages).  Ranks may hold different page counts: buffers are padded to ceil(n_pages / world) rows.  Returns the
+    results in GLOBAL PAGE ORDER (page p was decoded by rank p % world).
+    Transport: `ctx` given -> the library's NCCL all-gather (alm_gather_sequences; every rank gets the list);
+    otherwise torch.distributed (`dst` None -> all_gather, else gather to `dst`, None elsewhere)."""
+    if ctx is not None:
+        world, rank = ctx_world(ctx), None
+    else:
+        world, rank = dist.get_world_size(), dist.get_rank()
+    if n_pages is None:
+        n_pages = world * len(outs)
+    rows = pages_per_rank(n_pages, world)
+    assert len(outs) <= rows
     max_inst = max(1, vocab.pt_seq_length // 2)
-    buf = pack_sequences(outs, vocab, max_inst)
+    buf = pack_sequences(outs, vocab, max_inst, rows=rows)
+    if ctx is not None:
+        recv = torch.from_numpy(ctx.gather(buf.numpy(), world))
+        return interleave_pages([unpack_sequences(recv[r], vocab) for r in range(world)], n_pages)
     if device is None:
         device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
     buf = buf.to(device)
-    recv = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, recv, dst=dst)
-    if rank != dst:
-        return None
-    res = []
-    for r in recv:
-        res.extend(unpack_sequences(r.cpu(), vocab))
-    return res
+    if dst is None:
+        recv = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(recv, buf)
+    else:
+        recv = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, recv, dst=dst)
+        if rank != dst:
+            return None
+    return interleave_pages([unpack_sequences(r.cpu(), vocab) for r in recv], n_pages)
+
+
+def ctx_world(ctx) -> int:
+    return int(getattr(ctx, 'comm_world', 1))

@@ -72,13 +72,25 @@ class OmniParserB200:
     """Inference-only stand-in for the reference ``OmniParser`` module (``--tfm_pre_norm --use_fpn``)."""
 
     def __init__(self, state_dict, vocab: Optional[OmniVocab] = None, device: int = 0, stream: Optional[int] = None,
-                 ctx: Optional[_lib.Context] = None, workspace_mb: Optional[int] = None):
+                 ctx: Optional[_lib.Context] = None, workspace_mb: Optional[int] = None,
+                 share_from: Optional['OmniParserB200'] = None):
+        """state_dict: the reference checkpoint ``torch.load(path)['model']``; or None together with
+        ``share_from=other`` (another OmniParserB200 on the same GPU): this instance becomes a second execution
+        context over the SAME device weights (alm_share_weights) -- one model, several batches in flight; or None
+        when the weights were already put into ``ctx`` (multi-GPU start-up, dist.load_weights_broadcast).
+
+        Device inputs: the context enqueues on its own stream; CUDA tensors handed to encode()/forward() are ordered
+        after torch's current stream automatically (alm_stream_wait)."""
         self.vocab = vocab or OmniVocab()
         self.ctx = ctx or _lib.Context(device, stream)
         if workspace_mb:
             self.ctx.set_option('workspace_mb', workspace_mb)
-        kind = _lib.MODEL_OMNI_KIE if self.vocab.vie_categories else _lib.MODEL_OMNI_SPOT
-        self.ctx.load_state_dict(kind, state_dict)
+        if share_from is not None:
+            assert state_dict is None, 'pass either a state dict or share_from'
+            self.ctx.share_weights(share_from.ctx)
+        elif state_dict is not None:
+            kind = _lib.MODEL_OMNI_KIE if self.vocab.vie_categories else _lib.MODEL_OMNI_SPOT
+            self.ctx.load_state_dict(kind, state_dict)
         self.lib = self.ctx.lib
 
     # nn.Module look-alikes so reference drivers keep working
@@ -104,6 +116,7 @@ class OmniParserB200:
                 self._keep_mask = m8
                 mp = m8.data_ptr()
         self._keep_img = t
+        self.ctx.wait_torch(t, mask)  # device inputs: order the context's stream after torch's current stream
         self.ctx.check(self.lib.alm_omni_encode(self.ctx.h, t.data_ptr(), mp, B, H, W))
         return self.memory_shape()
 
@@ -163,6 +176,21 @@ class OmniParserB200:
                           torch.from_numpy(rec[b, :n][None].copy())],
                          [torch.from_numpy(prob[b, :n].copy())]))
         return outs
+
+    def decode_points(self, pt_prompt: Optional[torch.Tensor] = None):
+        """`decode_pt_seq` alone (model/transformer.py:102-141) for every encoded image: list of (tokens int64 [n],
+        probs f32 [n]) -- the long single-sequence decode of structure heads (BASELINE config 5: 512 tokens)."""
+        v = self.vocab
+        B, _, _ = self.memory_shape()
+        prompt = (pt_prompt if pt_prompt is not None else v.pt_prompt()).reshape(-1).to(torch.long).cpu().contiguous()
+        P = v.pt_seq_length
+        n_tok = np.zeros(B, dtype=np.int32)
+        toks = np.zeros((B, P), dtype=np.int64)
+        prob = np.zeros((B, P), dtype=np.float32)
+        cfg = self._cfg(max(1, P // 2))
+        self.ctx.check(self.lib.alm_omni_decode_points(self.ctx.h, prompt.data_ptr(), prompt.numel(), C.byref(cfg),
+                                                       n_tok.ctypes.data, toks.ctypes.data, prob.ctypes.data))
+        return [(torch.from_numpy(toks[b, :n_tok[b]].copy()), torch.from_numpy(prob[b, :n_tok[b]].copy())) for b in range(B)]
 
     def decode_kie(self, image_sizes, pt_prompt: Optional[torch.Tensor] = None):
         """KIE decoding of every encoded image (model/transformer.py:143-217): per image the reference's

@@ -72,6 +72,7 @@ def omni_pages(ctx: _lib.Context, images: List, test_min_size: int, test_max_siz
     dev = torch.device('cuda', ctx.device)
     tensors = torch.empty(n, 3, Hc, Wc, dtype=torch.float32, device=dev)
     mask = torch.empty(n, Hc, Wc, dtype=torch.uint8, device=dev)
+    ctx.wait_torch(*keep)
     ctx.check(ctx.lib.alm_pre_omni_pages(ctx.h, ptrs, hs.ctypes.data, ws.ctypes.data, n, test_min_size, test_max_size,
                                          tensors.data_ptr(), mask.data_ptr()))
     ctx.synchronize()
@@ -82,6 +83,7 @@ def mgp_crops(ctx: _lib.Context, images: List, imgH: int = 32, imgW: int = 128) 
     """[n,3,imgH,imgW] f32 in [0,1] on the device: `img.resize((imgW, imgH), Image.BICUBIC)` + ToTensor per crop."""
     keep, ptrs, hs, ws, n = _image_args(images)
     out = torch.empty(n, 3, imgH, imgW, dtype=torch.float32, device=torch.device('cuda', ctx.device))
+    ctx.wait_torch(*keep)
     ctx.check(ctx.lib.alm_pre_mgp_crops(ctx.h, ptrs, hs.ctypes.data, ws.ctypes.data, n, imgH, imgW, out.data_ptr()))
     ctx.synchronize()
     return out

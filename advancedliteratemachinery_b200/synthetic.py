@@ -143,8 +143,14 @@ MGP_MAXLEN = 27
 MGP_CHAR, MGP_BPE, MGP_WP = 38, 50257, 30522
 
 
+# the four released sizes (OCR/MGP-STR/modules/mgp_str.py:176-230): embed dim, depth, heads
+MGP_VARIANTS = {'tiny': (192, 12, 3), 'small': (384, 12, 6), 'base': (768, 12, 12), 'large': (1024, 24, 16)}
+
+
 def mgpstr_state_dict(seed: int = 0, prefix: str = 'module.mgp_str.', dim: int = VIT_DIM,
-                      depth: int = VIT_DEPTH, heads: int = VIT_HEADS):
+                      depth: int = VIT_DEPTH, heads: int = VIT_HEADS, char_only: bool = False):
+    """char_only: the CHAR-STR ablation (modules/char_str.py:43-81): one A^3 module; the logits come from timm's
+    `head` (char_str.py:70), `char_head` exists after reset_classifier but is never called."""
     g = _Gen(seed + 7919)
     sd = OrderedDict()
     sd['cls_token'] = g.normal((1, 1, dim), 0.5)
@@ -160,7 +166,7 @@ def mgpstr_state_dict(seed: int = 0, prefix: str = 'module.mgp_str.', dim: int =
         _linear(sd, g, q + 'mlp.fc2', dim, 4 * dim)
     _ln(sd, g, 'norm', dim)          # present in the checkpoints, never applied (mgp_str.py:64-94)
     _linear(sd, g, 'head', MGP_CHAR, dim)  # timm's classifier, unused as well
-    for a in ('char', 'bpe', 'wp'):
+    for a in (('char',) if char_only else ('char', 'bpe', 'wp')):
         q = f'{a}_tokenLearner.'
         _ln(sd, g, q + 'token_norm', dim)
         sd[q + 'tokenLearner.0.weight'] = g.uniform((dim, dim // 8, 1, 1), 1.0 / math.sqrt(dim // 8))
@@ -168,6 +174,7 @@ def mgpstr_state_dict(seed: int = 0, prefix: str = 'module.mgp_str.', dim: int =
         sd[q + 'feat.weight'] = g.uniform((dim, dim // 8, 1, 1), 1.0 / math.sqrt(dim // 8))
         _ln(sd, g, q + 'norm', dim)
     _linear(sd, g, 'char_head', MGP_CHAR, dim, gain=4.0)
-    _linear(sd, g, 'bpe_head', MGP_BPE, dim, gain=4.0)
-    _linear(sd, g, 'wp_head', MGP_WP, dim, gain=4.0)
+    if not char_only:
+        _linear(sd, g, 'bpe_head', MGP_BPE, dim, gain=4.0)
+        _linear(sd, g, 'wp_head', MGP_WP, dim, gain=4.0)
     return OrderedDict((prefix + k, v) for k, v in sd.items())

@@ -1,15 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- OCR forward hot path, BASELINE.json config 2:
-OmniParser Swin-B text spotting, 1024x1024 synthetic pages, batch 16 per GPU, N = 64 text instances per
-page pinned (pt_seq_length 128, 32 polygon + 25 recognition tokens per instance).
+"""bench.py -- the OCR forward hot path on B200, one JSON line per run (rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A step = one batch of 16 pages through Swin-B -> FPN -> input_proj -> pt/poly/rec greedy decoding.
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same metric through the
-adapter (`OmniParserB200.forward_batch`) with pinned HOST inputs, H2D and D2H inside the timed region.
-`--impl reference` times the CPU oracle port (the reference algorithm, no KV cache, all host threads) on a
-bounded sample of the same workload (the oracle is the checker everywhere else; this leg only times it).
+Workloads (BASELINE.json `configs`; the default is the one the headline metric is quoted on):
+
+  omni      config 2: OmniParser Swin-B text spotting, 1024x1024 synthetic pages, batch 16 per GPU, N = 64 text
+            instances per page pinned (pt_seq_length 128, 32 polygon + 25 recognition tokens each)
+  mgpstr    config 3: MGP-STR ViT-Base, 512 32x128 crops per GPU per step, bf16 (single-pass; --nsplit 3 = parity mode)
+  table     config 5: OmniParser at 1920x1920, 8 pages per GPU, one 512-token point-decoder sequence per page
+            (the table head itself is not released, SURVEY F4: the generic pt decoder is what is timed)
+  platypus  config 4: Platypus ships no code: the OmniParser encoder + decoder at 896x896, 8 pages per GPU
+            (32 over 4 GPUs), throughput only, NO parity oracle
+
+A step = one batch through the whole path.  `value`: inputs resident in HBM; `e2e`: the same metric through the adapter
+with pinned HOST inputs, H2D and D2H inside the timed region.  With N > 1 GPUs every step ends with ONE all-gather of the
+decoded sequences (alm_gather_sequences, the library's own NCCL communicator) inside the timed region, and the weights
+reach the ranks by ONE NCCL broadcast of the converted planes (alm_broadcast_weights).
+
+`--impl reference` times the reference algorithm (the CPU oracle port: fp32, no KV cache, memory repeated per instance,
+transformer.py:74-100) on the host cores on the SAME workload: one page (omni / table / platypus) or 32 crops (mgpstr)
+per step.  A full config-2 page costs the no-cache loops ~1.5-3 minutes of CPU, so the arm runs at most 3 timed steps
+(and reports the steps it actually ran); the oracle is the checker everywhere else, this leg only times it.
 """
 from __future__ import annotations
 
@@ -24,17 +36,41 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-PAGE = 1024
-BATCH = 16
-N_INST = 64
 REC_LEN = 25
-ENC_GFLOP_PER_IMAGE = 682.1   # SURVEY.md section 8d, algorithmic 2*M*N*K of the Swin-B encoder at 1024^2
-DOMINANT_GEMM = (65536, 2048, 512)  # stage-2 fc1 at batch 16 (M, N, K): stage 2 carries 494 of the 682 GF
+N_INST = 64
+ENC_GFLOP = {1024: 682.1, 896: 493.8, 1920: 2335.7}   # algorithmic 2*M*N*K of the Swin-B encoder per image
+MGP_GFLOP_PER_CROP = 49.75
+
+WORKLOADS = {
+    'omni': dict(kind='omni', page=1024, batch=16, n_inst=N_INST, pt_len=2 * N_INST, points_only=False, inflight=5,
+                 workspace_mb=20480, gemm=(65536, 2048, 512), gemm_name='Swin stage-2 fc1',
+                 text=f'OmniParser Swin-B text spotting, 1024x1024 synthetic pages, batch 16 per GPU, N={N_INST} '
+                      f'instances/page pinned (pt 128 + poly 32 + rec {REC_LEN} tokens)'),
+    'platypus': dict(kind='omni', page=896, batch=8, n_inst=N_INST, pt_len=2 * N_INST, points_only=False, inflight=5,
+                     workspace_mb=16384, gemm=(25088, 2048, 512), gemm_name='Swin stage-2 fc1',
+                     text=f'Platypus stand-in (no reference code, SURVEY F3): OmniParser encoder + decoder, 896x896 synthetic '
+                          f'pages, batch 8 per GPU, N={N_INST} instances/page; throughput only, no parity oracle'),
+    'table': dict(kind='omni', page=1920, batch=8, n_inst=0, pt_len=512, points_only=True, inflight=2,
+                  workspace_mb=40960, gemm=(115200, 2048, 512), gemm_name='Swin stage-2 fc1',
+                  text='OmniParser 1920x1920 synthetic pages, batch 8 per GPU, one 512-token point-decoder sequence per page '
+                       '(table head not released, SURVEY F4: generic pt decoder)'),
+    'mgpstr': dict(kind='mgp', batch=512, inflight=2, gemm=(131584, 3072, 768), gemm_name='ViT fc1',
+                   text='MGP-STR ViT-Base, 512 synthetic 32x128 crops per GPU per step, ids + probabilities of the three heads'),
+}
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant GEMM launch from the committed ncu capture."""
-    p = os.path.join(REPO, 'profiles', 'r01_prof_gemm_fc1_metrics.csv')
+# ---------------------------------------------------------------------------------------------------- utilities
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['bf16_tflops'], d['bf16_tflops_sustained'], d['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
+    return 1590.0, 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic_bytes(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant GEMM launch from a committed ncu capture."""
+    p = os.path.join(REPO, 'profiles', name)
     try:
         tot = 0.0
         for line in open(p):
@@ -44,28 +80,6 @@ def ncu_traffic_bytes():
         return tot or None
     except Exception:
         return None
-
-
-def pick_inflight(steps):
-    """Contexts in flight for a K-step timed region: steps are pulled from a shared counter, so K steps over C contexts
-    run as rounds of C (the last one possibly partial).  Measured ms per batch with n batches in flight (config 2,
-    tools/concurrency_probe.py): fuller rounds are cheaper, a nearly empty tail round is expensive."""
-    per_batch = {1: 190.0, 2: 165.0, 3: 150.0, 4: 143.0, 5: 141.0, 6: 140.0}
-    best, best_cost = 1, float('inf')
-    for c in range(1, 7):
-        full, tail = divmod(steps, c)
-        cost = full * c * per_batch[c] + (tail * per_batch[tail] if tail else 0.0)
-        if cost < best_cost - 1e-9:
-            best, best_cost = c, cost
-    return best
-
-
-def peaks():
-    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return d['bf16_tflops'], d['bf16_tflops_sustained'], d['hbm_gbs'], 'measured'
-    return 1590.0, 1400.0, 6650.0, 'fallback'
 
 
 class ClockSampler:
@@ -120,169 +134,322 @@ def effective_cpus():
     return max(1, min(n, 64)), {'affinity': len(os.sched_getaffinity(0)), 'cgroup_quota': quota, 'cpu_count': os.cpu_count()}
 
 
-CPU_SAMPLES = [  # (page side, pt_seq_length, subprocess timeout s) -- first one that finishes in time is reported
-    (PAGE, 4, 150),
-    (512, 2, 100),
-]
+def page_tensor(side, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(1, 3, side, side, generator=g)
 
 
-def _cpu_sample_child(side, pt_len):
-    """Runs in a subprocess: the reference algorithm (CPU oracle port: fp32, no KV cache, memory repeated per
-    instance, transformer.py:74-100) on ONE page; prints seconds."""
+def workload_config(name, world, nsplit):
+    """The `config` object: identical for the GPU arm and the reference arm of a workload."""
+    w = WORKLOADS[name]
+    return {'workload': w['text'], 'global_batch': world * w['batch'], 'parallelism': f'dp{world}',
+            'inputs': 'synthetic, seeded per page / crop (page p of the job: seed 1000 + p)',
+            'weights': 'synthetic seed 0 (advancedliteratemachinery_b200/synthetic.py)' +
+                       (', pt_eos suppressed so that every page decodes the pinned length' if w['kind'] == 'omni' else ''),
+            'l2': 'no explicit flush: per-step inputs and activations exceed the 126 MB L2'}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference
+def _cpu_child(name, n_inst, pt_len):
+    """Subprocess body: ONE unit of the reference algorithm on the host cores (oracle port); prints seconds."""
     import torch
     from advancedliteratemachinery_b200 import synthetic as W
-    from oracle import omniparser_ref as O
     torch.set_grad_enabled(False)
     threads, _ = effective_cpus()
     torch.set_num_threads(threads)
+    w = WORKLOADS[name]
+    if w['kind'] == 'mgp':
+        from oracle import mgpstr_ref as M
+        sd = W.mgpstr_state_dict(seed=0)
+        g = torch.Generator().manual_seed(1000)
+        img = torch.rand(n_inst, 3, 32, 128, generator=g)   # n_inst = crops in this sample
+        M.forward(img[:2], sd)                              # thread pool / allocator warm-up
+        t = time.time()
+        M.forward(img, sd)
+        print(json.dumps({'sec': time.time() - t, 'threads': torch.get_num_threads()}), flush=True)
+        return
+    from oracle import omniparser_ref as O
     sd = W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0)
-    g = torch.Generator().manual_seed(1000)
-    img = torch.randn(1, 3, side, side, generator=g)
-    mask = torch.zeros(1, side, side, dtype=torch.bool)
+    img = page_tensor(w['page'], 1000)
+    mask = torch.zeros(1, w['page'], w['page'], dtype=torch.bool)
     t = time.time()
+    if w['points_only']:
+        mem, pos, kpm, _ = O.encode(img, mask, sd)
+        t_enc = time.time() - t
+        seq = O.default_prompts(True)[0]
+        t1 = time.time()
+        for _ in range(pt_len):  # decode_pt_seq, no cache (transformer.py:102-141): whole prefix + memory K/V per token
+            lg = O.decode_logits(seq, mem[0], kpm[0], pos[0], sd, 'pt')[:, -1, :]
+            seq = torch.cat([seq, lg[:, :1000].argmax(-1, keepdim=True)], 1)
+        print(json.dumps({'sec': time.time() - t, 'enc_sec': t_enc, 'step_sec': (time.time() - t1) / pt_len,
+                          'threads': torch.get_num_threads()}), flush=True)
+        return
     O.forward(img, mask, sd, pt_seq_length=pt_len, rec_length=REC_LEN)
     print(json.dumps({'sec': time.time() - t, 'threads': torch.get_num_threads()}), flush=True)
 
 
-def cpu_reference_sample():
-    """Bounded CPU baseline: returns dict(value images/s, cores, sample, ...) or value None when even the
-    smallest sample exceeds its budget on this host."""
+def cpu_sample(name, n_inst, pt_len, timeout):
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-child', name, str(n_inst), str(pt_len)],
+                           capture_output=True, text=True, timeout=timeout, cwd=REPO)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {'error': type(e).__name__}
+
+
+def cpu_baseline_bounded(name):
+    """The bounded (10-30 s) CPU sample printed next to the GPU number: a REDUCED unit of the workload, stated as such.
+    The like-for-like CPU number is the `--impl reference` arm."""
     threads, info = effective_cpus()
-    for side, pt_len, tmo in CPU_SAMPLES:
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-sample', str(side), str(pt_len)],
-                               capture_output=True, text=True, timeout=tmo, cwd=REPO)
-            d = json.loads(r.stdout.strip().splitlines()[-1])
-        except Exception as e:  # timeout or failure: try the smaller sample
-            last = f'{type(e).__name__}'
-            continue
-        scale = (side / PAGE) ** 2
-        return {'value': scale / d['sec'], 'unit': 'images/s', 'cores': d['threads'], 'kind': 'port',
-                'sample': f'1 page {side}x{side}, N={pt_len // 2} instance(s) (pt_seq_length {pt_len}), 32 poly + {REC_LEN} rec '
-                          f'tokens each, no-cache reference decode: {d["sec"]:.1f} s'
-                          + ('' if side == PAGE else f' (value scaled by area to {PAGE}x{PAGE} pages)'),
-                'host': info}
-    return {'value': None, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-            'sample': f'no sample finished inside its time box ({last})', 'host': info}
+    w = WORKLOADS[name]
+    if w['kind'] == 'mgp':
+        d = cpu_sample(name, 32, 0, 200)
+        val = 32 / d['sec'] if 'sec' in d else None
+        return {'value': val, 'unit': 'images/s', 'cores': d.get('threads', threads), 'kind': 'port',
+                'sample': f'32 crops, one forward of the reference algorithm (fp32): {d.get("sec", float("nan")):.1f} s', 'host': info}
+    if w['points_only']:
+        d = cpu_sample(name, 0, 4, 300)
+        val = None
+        if 'sec' in d:
+            val = 1.0 / (d['enc_sec'] + d['step_sec'] * w['pt_len'])
+        return {'value': val, 'unit': 'images/s', 'cores': d.get('threads', threads), 'kind': 'port',
+                'sample': f'1 page {w["page"]}x{w["page"]}: encoder {d.get("enc_sec", float("nan")):.1f} s + 4 no-cache point-decoder '
+                          f'tokens at {d.get("step_sec", float("nan")):.2f} s each; value = 1 / (encoder + {w["pt_len"]} x token time), i.e. '
+                          'EXTRAPOLATED from the first 4 tokens (later tokens are slower: the prefix grows)', 'host': info}
+    d = cpu_sample(name, 8, 16, 400)
+    return {'value': (1.0 / d['sec']) if 'sec' in d else None, 'unit': 'images/s', 'cores': d.get('threads', threads), 'kind': 'port',
+            'sample': f'1 page {w["page"]}x{w["page"]} at N=8 instances (pt 16 + poly 32 + rec {REC_LEN} tokens each; the GPU arm '
+                      f'decodes N={w["n_inst"]}): {d.get("sec", float("nan")):.1f} s of the no-cache reference algorithm; the same-workload '
+                      'number is the --impl reference arm', 'host': info}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    name = args.workload
+    w = WORKLOADS[name]
+    threads, info = effective_cpus()
     t0 = time.time()
-    cb = cpu_reference_sample()
-    ips = cb['value']
+    budget = args.ref_budget_s
+    if w['kind'] == 'mgp':
+        unit_n, n_inst, pt_len, unit_desc = 32, 32, 0, '32 crops per step (1/16 of a 512-crop batch)'
+        max_steps = args.steps
+    else:
+        unit_n, n_inst, pt_len = 1, w['n_inst'], w['pt_len']
+        unit_desc = (f'1 page per step (the reference is batch-1, engine/val.py:22): full workload, N={n_inst} instances, '
+                     f'pt {pt_len} + poly 32 + rec {REC_LEN} tokens, no KV cache') if not w['points_only'] else \
+                    f'1 page per step: encoder + {pt_len} no-cache point-decoder tokens'
+        max_steps = min(args.steps, 3)
+    # warm-up: one reduced unit (pays library loading, thread-pool start, allocator growth)
+    warm = cpu_sample(name, 2 if w['kind'] != 'mgp' else 4, 4 if w['kind'] != 'mgp' else 0, 600)
+    secs = []
+    for _ in range(max_steps):
+        if secs and (time.time() - t0) + secs[-1] > budget:
+            break
+        d = cpu_sample(name, n_inst, pt_len, 3600)
+        if 'sec' not in d:
+            break
+        secs.append(d['sec'])
+        threads = d.get('threads', threads)
+    world = args.gpus
+    if not secs:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference sample did not finish'}), flush=True)
+        return
+    med = sorted(secs)[len(secs) // 2]
+    ips = unit_n / med
+    cb = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+          'sample': f'{unit_desc}; {len(secs)} timed step(s) after 1 reduced warm-up unit ({warm.get("sec", float("nan")):.1f} s); '
+                    f'seconds per step: {[round(s, 1) for s in secs]}; value = median', 'host': info}
     line = {
-        'impl': 'reference', 'metric': 'doc_images_per_sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': (1e3 / ips) if ips else None,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'OmniParser Swin-B text spotting, {PAGE}x{PAGE} synthetic pages (CPU reference port, '
-                               f'bounded sample per step: see cpu_baseline.sample; the GPU arm decodes N={N_INST}/page)'},
-        'cpu_baseline': cb,
+        'impl': 'reference', 'metric': 'doc_images_per_sec', 'value': ips, 'unit': 'images/s', 'n_gpus': world,
+        'steps': len(secs), 'warmup': 1, 'requested_steps': args.steps, 'requested_warmup': args.warmup,
+        'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(name, world, args.nsplit), 'cpu_baseline': cb,
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'CPU arm: rank 0 only, host cores only; it does not scale with --gpus (one process, one page at a time)',
         'wall_s': time.time() - t0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def mgp_decoded_chars(ids):
+    """char-head tokens before '[s]' (id 1), position 0 dropped (demo.py:39-60): what `decoded-chars/s` counts."""
+    c = ids[0][:, 1:]
+    eos = (c == 1)
+    first = (eos.float().cumsum(1) == 0).sum(1)   # tokens before the first [s] (all 26 when there is none)
+    return int(first.sum())
+
+
+def self_check_omni(out0):
+    """Page 0 of rank 0 (page seed 1000) against the reference's own output (tests/golden/omni_config2_page0.npz,
+    written by oracle/gen_golden.py config2 from the unmodified reference).  Sequences that leave the reference are
+    counted; tests/test_gpu_omniparser.py judges every such flip against the reference top-1/top-2 gap."""
+    import numpy as np
+    p = os.path.join(REPO, 'tests', 'golden', 'omni_config2_page0.npz')
+    if out0 is None or not os.path.exists(p):
+        return {'checked': False}
+    gold = np.load(p)
+    (pt, poly, rec), _ = out0
+    n = gold['pt'].size // 2
+    same_pt = bool(np.array_equal(pt.numpy(), gold['pt']))
+    bad_poly = int((poly.numpy().reshape(n, 32) != gold['poly'].reshape(n, 32)).any(1).sum()) if same_pt else None
+    bad_rec = int((rec.numpy()[0] != gold['rec'][0]).any(1).sum()) if same_pt else None
+    ok = same_pt and bad_poly + bad_rec <= 3
+    return {'checked': True, 'against': 'reference output on page seed 1000 (tests/golden/omni_config2_page0.npz)',
+            'pt_ids_equal': same_pt, 'poly_sequences_differing': bad_poly, 'rec_sequences_differing': bad_rec,
+            'sequences': 2 * n + 1, 'ok': bool(ok)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=BATCH)
-    ap.add_argument('--nsplit', type=int, default=3, help='3 = fp32-class split operands (parity mode), 1 = bf16')
+    ap.add_argument('--workload', default='omni', choices=sorted(WORKLOADS))
+    ap.add_argument('--nsplit', type=int, default=0, help='3 = fp32-class split operands (parity mode), 1 = single-pass bf16; '
+                    'default: 3 for the OmniParser workloads, 1 for mgpstr (config 3 is stated in bf16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--grid-cap', type=int, default=0)
-    ap.add_argument('--inflight', type=int, default=0, help='independent batches in flight per GPU (one context + stream '
-                    '+ host thread each): the per-token decode loops are latency-bound, concurrent batches fill their '
-                    'launch gaps.  0 = choose 3..6 so that the K timed steps split into equally full rounds')
+    ap.add_argument('--inflight', type=int, default=0, help='execution contexts in flight per GPU (one stream + host thread '
+                    'each, ONE shared set of weights): the per-token decode loops are latency-bound, concurrent batches fill '
+                    'their launch gaps.  0 = the workload default')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
-    ap.add_argument('--cpu-sample', nargs=2, type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument('--ref-budget-s', type=float, default=330.0, help='reference arm: stop adding timed steps past this')
+    ap.add_argument('--cpu-child', nargs=3, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.cpu_sample:
-        return _cpu_sample_child(*args.cpu_sample)
+    if args.cpu_child:
+        return _cpu_child(args.cpu_child[0], int(args.cpu_child[1]), int(args.cpu_child[2]))
     if args.impl == 'reference':
         return run_reference(args)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from advancedliteratemachinery_b200 import NestedTensor, OmniParserB200, OmniVocab, _lib
-    from advancedliteratemachinery_b200.dist import broadcast_state_dict, gather_sequences
+    from advancedliteratemachinery_b200 import MGPSTRB200, NestedTensor, OmniParserB200, OmniVocab, _lib
+    from advancedliteratemachinery_b200.dist import gather_sequences, init_comm, load_weights_broadcast
     from advancedliteratemachinery_b200 import synthetic as W  # synthetic checkpoint (data only)
 
     torch.set_grad_enabled(False)
+    name = args.workload
+    w = WORKLOADS[name]
+    is_mgp = w['kind'] == 'mgp'
+    nsplit = args.nsplit or (1 if is_mgp else 3)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node N for --gpus N'
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        dist.init_process_group('nccl', device_id=dev)
 
-    # ---- weights: rank 0 builds the synthetic checkpoint, ONE NCCL broadcast of the packed weights
-    sd = W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0) if rank == 0 else None
-    if world > 1:
-        sd = broadcast_state_dict(sd, src=0, device=torch.device('cuda', local))
-    vocab = OmniVocab(pt_seq_length=2 * N_INST, rec_length=REC_LEN)
-    C_ = args.inflight if args.inflight > 0 else pick_inflight(args.steps)
+    # ---- contexts: ONE set of weights per GPU, C execution contexts over it
+    C_ = args.inflight if args.inflight > 0 else w['inflight']
+    C_ = max(1, min(C_, args.steps))
     streams = [torch.cuda.Stream() for _ in range(C_)]
-    ctxs, models = [], []
+    ctxs = []
     for j in range(C_):
         cx = _lib.Context(local, streams[j].cuda_stream)
-        cx.set_option('nsplit', args.nsplit)
-        cx.set_option('workspace_mb', 20480)
-        if args.grid_cap:
-            cx.set_option('small_grid_cap', args.grid_cap)
+        cx.set_option('nsplit', nsplit)
+        if not is_mgp:
+            cx.set_option('workspace_mb', w['workspace_mb'])
         for kv in args.opt:
             cx.set_option(kv.split('=')[0], int(kv.split('=')[1]))
         ctxs.append(cx)
-        models.append(OmniParserB200(sd, vocab, ctx=cx))
+    # weights: rank 0 builds the synthetic checkpoint; ONE NCCL broadcast of the converted planes (C ABI) to the others
+    kind = _lib.MODEL_MGPSTR if is_mgp else _lib.MODEL_OMNI_SPOT
+    sd = None
+    if rank == 0:
+        sd = W.mgpstr_state_dict(seed=0) if is_mgp else W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0)
+    t_w = time.time()
+    if world > 1:
+        for cx in ctxs:                      # one communicator per context, created in the same order on every rank
+            init_comm(cx, device=dev)
+        load_weights_broadcast(ctxs[0], kind, sd, src=0, device=dev)
+    else:
+        ctxs[0].load_state_dict(kind, sd)
+    weights_s = time.time() - t_w
     del sd
-    stream, ctx, model = streams[0], ctxs[0], models[0]
+    if is_mgp:
+        models = [MGPSTRB200(None, ctx=ctxs[0])] + [None] * (C_ - 1)
+        for j in range(1, C_):
+            ctxs[j].share_weights(ctxs[0])
+            models[j] = MGPSTRB200(None, ctx=ctxs[j])
+        vocab = None
+    else:
+        vocab = OmniVocab(pt_seq_length=w['pt_len'], rec_length=REC_LEN)
+        models = [OmniParserB200(None, vocab, ctx=ctxs[0])] + [None] * (C_ - 1)
+        for j in range(1, C_):
+            ctxs[j].share_weights(ctxs[0])
+            models[j] = OmniParserB200(None, vocab, ctx=ctxs[j])
+    ctx, model = ctxs[0], models[0]
 
-    B = args.batch
-    g = torch.Generator().manual_seed(1000 + rank * B)
-    host_pages = torch.randn(B, 3, PAGE, PAGE, generator=g).pin_memory()   # 201 MB > L2 (126 MB)
-    dev_pages = host_pages.cuda(non_blocking=False)
-    h2d_bytes = host_pages.numel() * 4
+    # ---- inputs: this rank's round-robin shard of the job's pages (page p -> rank p % world), seeded per page
+    B = w['batch']
+    pages = [rank + i * world for i in range(B)]
+    if is_mgp:
+        host_in = torch.cat([torch.rand(1, 3, 32, 128, generator=torch.Generator().manual_seed(1000 + p)) for p in pages])
+    else:
+        host_in = torch.cat([page_tensor(w['page'], 1000 + p) for p in pages])
+    host_in = host_in.pin_memory()
+    dev_in = host_in.cuda(non_blocking=False)
+    h2d_bytes = host_in.numel() * 4
 
-    def step_resident(j=0):
-        models[j].encode(dev_pages, None)
-        return models[j].decode()
+    def run_model(j, x):
+        if is_mgp:
+            return models[j].recognize(x)
+        models[j].encode(x, None)
+        return models[j].decode_points() if w['points_only'] else models[j].decode()
 
-    def step_e2e(j=0):
-        return models[j].forward_batch(NestedTensor(host_pages, None))
+    def gather(j, out):
+        """ONE all-gather of the decoded sequences of this step over the context's NCCL communicator."""
+        if world == 1:
+            return None
+        if is_mgp:
+            ids, prob = out
+            buf = np.concatenate([ids.numpy().reshape(-1), prob.numpy().view(np.int32).reshape(-1)])
+            return ctxs[j].gather(buf, world)
+        if w['points_only']:
+            buf = np.zeros((B, 1 + 2 * w['pt_len']), dtype=np.int32)
+            for b, (tok, pr) in enumerate(out):
+                buf[b, 0] = tok.numel()
+                buf[b, 1:1 + tok.numel()] = tok.numpy()
+                buf[b, 1 + w['pt_len']:1 + w['pt_len'] + tok.numel()] = pr.numpy().view(np.int32)
+            return ctxs[j].gather(buf, world)
+        return gather_sequences(out, vocab, n_pages=world * B, ctx=ctxs[j])
+
+    def step_resident(j):
+        out = run_model(j, dev_in)
+        return out, gather(j, out)
+
+    def step_e2e(j):
+        out = run_model(j, host_in)
+        return out, gather(j, out)
 
     def run_steps(fn, steps):
-        """`steps` batches, round-robin over the in-flight contexts (one host thread per context: the C calls
-        release the GIL, the per-context streams overlap on the device)."""
-        outs = [None] * C_
-        if C_ == 1:
-            for _ in range(steps):
-                outs[0] = fn(0)
-            return outs[0]
-        lock, nxt = threading.Lock(), [0]
+        """`steps` batches; step s runs on context s % C (static, so that the per-context collectives line up across
+        ranks).  One host thread per context: the C calls release the GIL, the per-context streams overlap on the device."""
+        last = [None] * C_
 
         def worker(j):
-            while True:
-                with lock:  # steps are pulled from a shared counter: exactly `steps` batches, no per-context quota
-                    if nxt[0] >= steps:
-                        return
-                    nxt[0] += 1
-                outs[j] = fn(j)
-        ts = [threading.Thread(target=worker, args=(j,)) for j in range(C_)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        return next(o for o in outs if o is not None)
+            for _ in range(j, steps, C_):
+                last[j] = fn(j)
+        if C_ == 1:
+            worker(0)
+        else:
+            ts = [threading.Thread(target=worker, args=(j,)) for j in range(C_)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return last
 
     def timed(fn, steps, warmup):
-        for j in range(C_):          # every context warms up (graph capture) ...
+        for j in range(C_):          # every context runs once (graph capture, descriptor caches) ...
             fn(j)
         run_steps(fn, warmup)        # ... then `warmup` untimed steps through the scheduler
         torch.cuda.synchronize()
@@ -296,7 +463,7 @@ def main():
         e0.record(streams[0])
         for j in range(1, C_):
             streams[j].wait_event(e0)
-        outs = run_steps(fn, steps)
+        last = run_steps(fn, steps)
         for j in range(C_):
             ends[j].record(streams[j])
         torch.cuda.synchronize()
@@ -307,42 +474,63 @@ def main():
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), sum(cx.launch_count(True) for cx in ctxs), outs
+        return float(t.item()), sum(cx.launch_count(True) for cx in ctxs), last
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches, outs = timed(step_resident, args.steps, args.warmup)
+    ms_total, launches, last = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, outs_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, last_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
 
-    # ---- one gather of the decoded sequences (int32, fixed stride) to rank 0 over NVLink
-    n_chars = sum(0 if o is None else o[0][2].numel() for o in outs)
-    d2h_bytes = sum(0 if o is None else sum(t.numel() * 8 for t in o[0]) + o[1][0].numel() * 4 for o in outs) + 4 * B
-    gathered = gather_sequences(outs, vocab, dst=0) if world > 1 else None
-    if world > 1 and rank == 0:
-        assert len(gathered) == world * B
+    out0, gathered0 = last[0]
+    # ---- what was decoded, and what crossed PCIe per step
+    if is_mgp:
+        n_chars = mgp_decoded_chars(out0[0])
+        d2h_bytes = out0[0].numel() * 4 + out0[1].numel() * 4
+    elif w['points_only']:
+        n_chars = sum(int(t.numel()) for t, _ in out0)
+        d2h_bytes = sum(int(t.numel()) * 12 for t, _ in out0) + 4 * B
+    else:
+        n_chars = sum(0 if o is None else o[0][2].numel() for o in out0)
+        d2h_bytes = sum(0 if o is None else sum(t.numel() * 8 for t in o[0]) + o[1][0].numel() * 4 for o in out0) + 4 * B
+
+    # ---- self-check of the timed run: rank 0's first page (page seed 1000) against the reference's own output; with
+    #      N > 1 also the all-gathered copy of that page and the global page count
+    check = None
+    if name == 'omni':
+        check = self_check_omni(out0[0])
+        if world > 1 and rank == 0:
+            check['gathered_pages'] = len(gathered0)
+            g0 = gathered0[0]
+            check['gathered_page0_equals_local'] = bool(g0 is not None and all(
+                torch.equal(a, b) for a, b in zip(g0[0], out0[0][0])))
+            check['ok'] = bool(check.get('ok')) and check['gathered_page0_equals_local'] and len(gathered0) == world * B
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), measured live with CUDA events on the ctx stream
-    M_, N_, K_ = DOMINANT_GEMM
-    # the Swin stage-2 fc1 launch exactly as the encoder issues it: GELU + split-bf16 epilogue (the ncu capture in
-    # profiles/r01_prof_gemm_fc1_metrics.csv is the same launch)
-    gemm_ms, _ = ctx.bench_gemm_ex(M_, N_, K_, 1, 1, 1, iters=20)
+    M_, N_, K_ = w['gemm']
+    gemm_ms, _ = ctx.bench_gemm_ex(M_, N_, K_, 1, 1, 1, iters=20)   # GELU + split-bf16 epilogue, as the model issues it
     burst, sustained, hbm, peak_src = peaks()
     achieved = 2.0 * M_ * N_ * K_ / (gemm_ms * 1e-3) / 1e12
     torch.cuda.synchronize()
-    step_resident(0)                       # one isolated step: per-phase device times without cross-batch contention
-    phase_ms = ctx.omni_last_timing()
+    phase_ms, enc_ms = None, None
+    step_resident(0)                       # one isolated step: device times without cross-batch contention
+    if not is_mgp:
+        phase_ms = ctx.omni_last_timing()
     ctx.set_option('profile_gemm', 1)
-    step_resident()
+    step_resident(0)
     g_ms, g_flops, g_n = ctx.profile_read()
     ctx.set_option('profile_gemm', 0)
     torch.cuda.synchronize()
-    t_enc0 = time.time()
-    model.encode(dev_pages, None)
-    model.memory_shape()
-    ctx.check(ctx.lib.alm_profile_read(ctx.h, None, None, None))   # stream sync
-    enc_ms = (time.time() - t_enc0) * 1e3
+    e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_a.record(streams[0])
+    if is_mgp:
+        model.recognize(dev_in)
+    else:
+        model.encode(dev_in, None)
+    e_b.record(streams[0])
+    torch.cuda.synchronize()
+    iso_ms = e_a.elapsed_time(e_b)
 
     if rank != 0:
         if world > 1:
@@ -352,34 +540,45 @@ def main():
     ms_per_step = ms_total / args.steps
     ips = world * B / (ms_per_step * 1e-3)
     ips_e2e = world * B / (ms_e2e / args.steps * 1e-3)
+    cfg = workload_config(name, world, nsplit)
     line = {
         'metric': 'doc_images_per_sec', 'value': ips, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None,
-        'dtype': 'bf16x3-split (fp32-class, fp32 accumulate)' if args.nsplit == 3 else 'bf16',
-        'data': 'synthetic',
-        'config': {'workload': f'OmniParser Swin-B text spotting, {PAGE}x{PAGE} synthetic pages, batch {B} per GPU, '
-                               f'N={N_INST} instances/page pinned (pt 128 + poly 32 + rec {REC_LEN} tokens)',
-                   'global_batch': world * B, 'parallelism': f'dp{world}', 'in_flight_batches_per_gpu': C_, **({'options': args.opt} if args.opt else {}), 'l2': 'inputs (201 MB/step) and activations '
-                   'exceed the 126 MB L2; no explicit flush', 'weights': 'synthetic seed 0 (advancedliteratemachinery_b200/synthetic.py), pt_eos pinned'},
+        'dtype': 'bf16x3-split (fp32-class, fp32 accumulate)' if nsplit == 3 else 'bf16',
+        'data': 'synthetic', 'config': cfg,
+        'run': {'in_flight_contexts_per_gpu': C_, 'weights_shared_by_contexts': True,
+                'weights_startup_s': weights_s, 'weights_path': 'alm_broadcast_weights (one NCCL broadcast of the converted '
+                'planes)' if world > 1 else 'alm_load_weights', 'gather': 'alm_gather_sequences inside every timed step'
+                if world > 1 else 'n/a (1 GPU)', **({'options': args.opt} if args.opt else {})},
         'decoded_chars_per_sec': world * n_chars / (ms_per_step * 1e-3),
-        'encoder_ms_per_batch': enc_ms,
-        'phase_ms': phase_ms,
-        'encoder_algorithmic_tflops': ENC_GFLOP_PER_IMAGE * B / enc_ms,
         'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
         'gpu_launches': launches,
         'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<256,3>' if args.nsplit == 3 else 'gemm_tcgen05_kernel<256,1>',
-                     'launch': 'Swin stage-2 fc1 (bias + GELU + split-bf16 output), timed alone with CUDA events',
+        'self_check': check,
+        'roofline': {'bound': 'tensor', 'kernel': f'gemm_tcgen05_kernel<256,{nsplit}>',
+                     'launch': f'{w["gemm_name"]} (bias + GELU + split-bf16 output), timed alone with CUDA events',
                      'shape': {'M': M_, 'N': N_, 'K': K_}, 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
-                     'frac': achieved / burst, 'traffic': ncu_traffic_bytes(),
-                     'algorithmic_bytes': float(M_ * K_ * 4 + N_ * K_ * 4 + M_ * N_ * 4), 'peak_source': f'{peak_src} bf16 burst (kernel timed alone)',
-                     'mma_passes_per_flop': args.nsplit, 'tensor_pipe_frac': achieved * args.nsplit / burst,
-                     'all_gemms_per_step': {'launches': g_n, 'ms': g_ms, 'algorithmic_tflops': g_flops / (g_ms * 1e-3) / 1e12 if g_ms else None,
-                                            'share_of_step': g_ms / ms_per_step if ms_per_step else None}},
+                     'frac': achieved / burst,
+                     'traffic': ncu_traffic_bytes('r01_prof_gemm_fc1_metrics.csv') if name == 'omni' else None,
+                     'algorithmic_bytes': float(M_ * K_ * 4 + N_ * K_ * 4 + M_ * N_ * 4) if nsplit == 3 else float(M_ * K_ * 2 + N_ * K_ * 2 + M_ * N_ * 4),
+                     'peak_source': f'{peak_src}, bf16 burst (kernel timed alone)',
+                     'mma_passes_per_flop': nsplit, 'tensor_pipe_frac': achieved * nsplit / burst,
+                     'all_gemms_per_step': {'launches': g_n, 'ms': g_ms,
+                                            'algorithmic_tflops': g_flops / (g_ms * 1e-3) / 1e12 if g_ms else None,
+                                            'frac_of_sustained_peak': (g_flops / (g_ms * 1e-3) / 1e12 / sustained) if g_ms else None}},
     }
+    if is_mgp:
+        line['forward_ms_per_batch_isolated'] = iso_ms
+        line['algorithmic_tflops'] = MGP_GFLOP_PER_CROP * B / iso_ms
+        line['frac_of_sustained_peak'] = MGP_GFLOP_PER_CROP * B / iso_ms / sustained
+    else:
+        line['phase_ms'] = phase_ms
+        line['encoder_ms_per_batch'] = iso_ms
+        line['encoder_algorithmic_tflops'] = ENC_GFLOP[w['page']] * B / iso_ms
+        line['encoder_frac_of_sustained_peak'] = ENC_GFLOP[w['page']] * B / iso_ms / sustained
     if not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_reference_sample()
+        line['cpu_baseline'] = cpu_baseline_bounded(name)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

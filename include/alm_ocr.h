@@ -196,6 +196,14 @@ ALM_API int alm_omni_memory_shape(alm_ctx* ctx, int* B, int* h, int* w);
 ALM_API int alm_omni_decode(alm_ctx* ctx, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg, int32_t* n_inst,
                     int64_t* pt, int64_t* poly, int64_t* rec, float* rec_prob);
 
+/* The point loop alone: `decode_pt_seq` (transformer.py:102-141) for every encoded image -- the structure / layout
+ * sequence decoders built on this model (the unreleased table-recognition head, OCR/OmniParser/README.md:85-101) run
+ * exactly this loop for hundreds of tokens.  Outputs (host), per image b: n_tok[b] generated tokens (prompt stripped,
+ * a trailing odd token dropped as in :138-139), pt_tokens[b, pt_seq_length] int64, pt_probs[b, pt_seq_length] f32
+ * (may be NULL).  max_instances / poly_length of cfg are ignored. */
+ALM_API int alm_omni_decode_points(alm_ctx* ctx, const int64_t* pt_prompt, int n_prompt, const alm_decode_cfg* cfg,
+                                   int32_t* n_tok, int64_t* pt_tokens, float* pt_probs);
+
 /* KIE variant (--infer_vie): replaces the eval branch with `decode_vie_pt_poly_rec_seq` (transformer.py:143-217,243-246).
  * The pt loop emits (x, y, class) triples (:117-123) with the class slot restricted to the last vie_categories
  * ids; every (x, y) pair found by the reference's walk (:148-210) gets a polygon and a transcription whose
@@ -222,7 +230,12 @@ ALM_API int alm_omni_last_timing(alm_ctx* ctx, float* encode_ms, float* pt_ms, f
  * img: f32 [B,3,32,128] in [0,1].  Any output pointer may be NULL.  Host buffers:
  *   attn   [3][B,27,257] f32 (char, bpe, wp A^3 maps)
  *   char_logits [B,27,38], bpe_logits [B,27,50257], wp_logits [B,27,30522]  f32
- *   ids    [3][B,27] int32 top-1 ids, prob [3][B,27] f32 max softmax prob (demo.py:36-60). */
+ *   ids    [3][B,27] int32 top-1 ids, prob [3][B,27] f32 max softmax prob (demo.py:36-60).
+ * The model variant comes from the checkpoint: tiny / small / base / large (embed 192 / 384 / 768 / 1024, 64-wide heads,
+ * mgp_str.py:176-230) and the char-only CHAR-STR ablation (modules/char_str.py:43-81: one A^3 module, logits through
+ * timm's `head`).  For CHAR-STR only the first plane of attn / ids / prob and char_logits are written; the class
+ * counts of the heads (the widths of the logit buffers) are reported by alm_mgpstr_info. */
+ALM_API int alm_mgpstr_info(alm_ctx* ctx, int* dim, int* depth, int* heads, int* n_a3, int* vocab3 /*[3]*/);
 ALM_API int alm_mgpstr_forward(alm_ctx* ctx, const float* img, int B, float* attn, float* char_logits, float* bpe_logits,
                        float* wp_logits, int32_t* ids, float* prob);
 

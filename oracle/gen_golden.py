@@ -289,6 +289,48 @@ def gen_mgp():
         print(f'mgp_{name}: ok')
 
 
+# the other released sizes (mgp_str.py:176-230) and the CHAR-STR ablation (char_str.py:43-81), B = 2 each
+MGP_VARIANT_CASES = {'tiny': dict(seed=21), 'small': dict(seed=22), 'large': dict(seed=23), 'charstr': dict(seed=24)}
+
+
+def gen_mgp_variants():
+    """tiny / small / large MGP-STR and base CHAR-STR: the reference classes are instantiated directly (the tiny / small
+    factories download DeiT weights unconditionally, mgp_str.py:216,228), loaded strict=True with the synthetic
+    checkpoint of that size, and compared with the restatement."""
+    sys.path[:0] = [SHIM, os.path.join(REF, 'MGP-STR')]
+    from oracle import mgpstr_ref as M
+    from oracle import weights as W
+    from modules.mgp_str import MGPSTR
+    from modules.char_str import CHARSTR
+    for name, case in MGP_VARIANT_CASES.items():
+        char_only = name == 'charstr'
+        dim, depth, heads = W.MGP_VARIANTS['base' if char_only else name]
+        cls = CHARSTR if char_only else MGPSTR
+        model = cls(batch_max_length=27, img_size=(32, 128), patch_size=4, embed_dim=dim, depth=depth, num_heads=heads,
+                    mlp_ratio=4, qkv_bias=True, in_chans=3, num_classes=38)
+        model.reset_classifier(num_classes=38)
+        model.eval()
+        sd = W.mgpstr_state_dict(seed=case['seed'], dim=dim, depth=depth, heads=heads, char_only=char_only)
+        r = model.load_state_dict({k[len('module.mgp_str.'):]: v for k, v in sd.items()}, strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        g = torch.Generator().manual_seed(case['seed'])
+        img = torch.rand(2, 3, 32, 128, generator=g)
+        with torch.no_grad():
+            out = model(img, is_eval=True)
+            o = M.forward(img, sd, depth=depth, heads=heads)
+        for a, b in zip(out[0], o[0]):
+            assert _maxdiff(a, b) < 1e-6
+        for a, b in zip(out[1:], o[1:]):
+            assert _maxdiff(a, b) < 2e-5, (name, _maxdiff(a, b))
+        gold = dict(char=out[1].numpy(), char_attn=out[0][0].numpy(), dims=np.array([dim, depth, heads]))
+        if not char_only:
+            for nm, lg in (('bpe', out[2]), ('wp', out[3])):
+                gold[nm + '_ids'] = lg.argmax(-1).numpy()
+                gold[nm + '_s'] = lg.reshape(-1)[::997].numpy()
+        np.savez_compressed(os.path.join(GOLD, f'mgp_{name}.npz'), **gold)
+        print(f'mgp_{name}: ok  dim={dim} depth={depth} heads={heads}')
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     os.makedirs(GOLD, exist_ok=True)
@@ -302,5 +344,7 @@ if __name__ == '__main__':
         gen_kie()
     elif which == 'config2':
         gen_config2()
+    elif which == 'mgpvar':
+        gen_mgp_variants()
     else:
         gen_mgp()

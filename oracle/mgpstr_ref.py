@@ -61,6 +61,9 @@ def forward(img, sd, prefix='module.mgp_str.', depth=W.VIT_DEPTH, heads=W.VIT_HE
     wp [B,27,30522]]   (mgp_str.py:96-101 with is_eval=True)."""
     x, sd = backbone(img, sd, prefix, depth, heads)
     attns, outs = [], []
+    if 'bpe_tokenLearner.token_norm.weight' not in sd:  # CHAR-STR (modules/char_str.py:56-81): logits through `head`
+        sel, y = token_learner(x, sd, 'char_tokenLearner.')
+        return [[sel], F.linear(y, sd['head.weight'], sd['head.bias'])]
     for a in ('char', 'bpe', 'wp'):
         sel, y = token_learner(x, sd, f'{a}_tokenLearner.')
         attns.append(sel)

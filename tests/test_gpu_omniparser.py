@@ -1,9 +1,11 @@
 """GPU parity: OmniParser CUDA path (through the C ABI) vs the CPU oracle and the committed reference
 fixtures.  Tolerances (north_star): logits within 1e-3 relative, argmax token ids identical.
 
-Protocol for ids ("parity vs precision"): greedy ids must equal the reference's; a
-mismatch is tolerated only if the reference's own top-1/top-2 gap at that step is below 10x the measured
-logit error (random synthetic weights have near-ties) -- teacher-forced logits are always checked.
+Protocol for ids ("parity vs precision"): the small fixtures are generated free of near-ties and
+must match bit for bit.  At benchmark scale (3 776 greedy steps per page) random synthetic weights do produce steps whose
+reference top-1/top-2 gap is at the level of fp32 accumulation-order noise; there a mismatch is tolerated only if the
+reference gap at that step is below 10x the measured logit error AND the CUDA path picked the reference runner-up, every
+such flip is printed, and the count is bounded (MAX_NEAR_TIE_FLIPS).  Teacher-forced logits are always checked.
 """
 import os
 
@@ -169,55 +171,14 @@ def test_decode_matches_reference_fixture(name, golden_dir):
     rec_full = torch.cat([gpt.reshape(-1, 2), torch.full((n, 1), v.rec_sos_index), torch.from_numpy(gold['rec'])[0]], 1)
     lg = m.decode_logits(0, 'rec', rec_full)
     assert _maxrel(lg[:, [2, 2 + L // 2, 2 + L - 1]], torch.from_numpy(gold['tf_rec'])) < LOGIT_REL_TOL
-    # greedy ids: bit-exact, except where the REFERENCE itself has a near-tie (top-1/top-2 gap below 10x our measured
-    # logit error at that step: random synthetic weights produce a few of those; after such a flip the two greedy
-    # sequences legitimately diverge, so only the first difference of each sequence is judged)
-    from oracle import omniparser_ref as O
-    from tests.conftest import omni_sd
-    sd = omni_sd(case['wseed'], case['pt_eos_bias'])
-
-    def allowed_mask(kind, step):
-        a = torch.zeros(v.num_classes, dtype=torch.bool)
-        if kind == 'pt':
-            a[:v.num_bins] = True
-            if step % 2 == 0:
-                a[v.pt_eos_index] = True
-        elif kind == 'poly':
-            a[:v.num_bins] = True
-        else:
-            a[v.num_bins:v.recog_pad_index + 1] = True
-            a[v.rec_eos_index] = True
-        return a
-
-    def ids_match_or_near_tie(kind, got_rows, gold_rows, gold_full, n_prompt):
-        if np.array_equal(got_rows, gold_rows):
-            return True
-        mem_o, pos_o, kpm_o, _ = O.encode(img, mask, sd)
-        ref_lg = O.decode_logits(gold_full, mem_o[0], kpm_o[0], pos_o[0], sd, kind)
-        our_lg = m.decode_logits(0, kind, gold_full)
-        for s_ in range(gold_rows.shape[0]):
-            diff = np.nonzero(got_rows[s_] != gold_rows[s_])[0]
-            if diff.size == 0:
-                continue
-            t = int(diff[0])
-            p_ = n_prompt - 1 + t
-            a = allowed_mask(kind, t)
-            r = ref_lg[s_, p_].clone()
-            r[~a] = -1e30
-            top = r.topk(2)
-            gap = float(top.values[0] - top.values[1])
-            err = float((our_lg[s_, p_] - ref_lg[s_, p_]).abs().max())
-            assert gap < 10 * max(err, 1e-6), f'{kind} seq {s_} step {t}: reference gap {gap:.2e} vs logit error {err:.2e}'
-            assert int(got_rows[s_, t]) == int(top.indices[1]), 'a near-tie flip must pick the reference runner-up'
-        return False
-
-    pt_ok = ids_match_or_near_tie('pt', pt.numpy(), gold['pt'], torch.cat([v.pt_prompt(), gpt], 1), 7)
-    if not pt_ok:
-        return  # the instance set itself changed at a reference near-tie; nothing below is comparable
-    poly_ok = ids_match_or_near_tie('poly', poly.numpy().reshape(n, 32), gold['poly'].reshape(n, 32), poly_full, 3)
-    rec_ok = ids_match_or_near_tie('rec', rec.numpy()[0], gold['rec'][0], rec_full, 3)
-    if not (poly_ok and rec_ok):
-        return
+    # greedy ids: BIT-EXACT.  The fixtures are generated with a near-tie floor (oracle/gen_golden.py GAP_FLOOR: every
+    # greedy step of the reference has a top-1/top-2 logit gap >= 1e-4, ~7x the CUDA path's measured logit error), so
+    # there is no near-tie excuse here; the near-tie protocol only exists in the page-scale test below, where it counts,
+    # prints and bounds the flips.
+    assert float(gold['min_gap'].min()) >= 1e-4
+    assert np.array_equal(pt.numpy(), gold['pt']), 'pt ids differ from the reference'
+    assert np.array_equal(poly.numpy(), gold['poly']), 'poly ids differ from the reference'
+    assert np.array_equal(rec.numpy(), gold['rec']), 'rec ids differ from the reference'
     np.testing.assert_allclose(probs.numpy(), gold['probs'], rtol=2e-3, atol=1e-7)
     # the post-processing contract (utils/misc.py:164-185) on our ids gives the reference strings
     from oracle import omniparser_ref as O
@@ -512,3 +473,249 @@ def test_config5_geometry_largest_page_and_long_point_sequence():
     m.vocab.pt_seq_length = 64
     out = m.decode()
     assert out[0] is not None and out[0][0][0].numel() == 64      # eos is pinned off: the full sequence is produced
+
+
+# ----------------------------------------------------------------------------------------------- benchmark scale
+MAX_NEAR_TIE_FLIPS = 3   # sequences (of 129 per page) allowed to leave the reference at a judged near-tie
+
+
+def _first_diffs(got, gold):
+    """[(row, first differing step)] for two [rows, steps] id arrays."""
+    out = []
+    for r in range(gold.shape[0]):
+        d = np.nonzero(got[r] != gold[r])[0]
+        if d.size:
+            out.append((r, int(d[0])))
+    return out
+
+
+def _judge_flips(kind, got, gold, gaps, ref_logits, our_logits, start, cands):
+    """Every sequence whose ids leave the reference must do so at a reference near-tie: gap < 10 x the measured logit
+    error at that position, and the id picked is the reference runner-up.  Returns printable flip records."""
+    flips = []
+    for r, t in _first_diffs(got, gold):
+        pos = start - 1 + t
+        err = float((our_logits[r, pos] - ref_logits[r, pos]).abs().max())
+        lg = ref_logits[r, pos].masked_fill(~cands(kind, t, ref_logits.shape[-1]), float('-inf'))
+        top = lg.topk(2)
+        gap = float(top.values[0] - top.values[1])
+        assert abs(gap - float(gaps[r, t])) < 1e-4, 'oracle gap differs from the fixture gap'
+        assert gap < 10 * max(err, 1e-6), f'{kind} seq {r} step {t}: reference gap {gap:.2e} vs logit error {err:.2e} -- a real mismatch'
+        assert int(got[r, t]) == int(top.indices[1]), f'{kind} seq {r} step {t}: not the reference runner-up'
+        flips.append(dict(kind=kind, seq=r, step=t, ref_gap=gap, logit_err=err))
+    return flips
+
+
+def test_config2_scale_decode_matches_the_reference(golden_dir):
+    """BASELINE config 2 at full scale, against the UNMODIFIED reference's output on the same page (fixture
+    omni_config2_page0.npz: oracle/gen_golden.py config2, 164 s of CPU for the no-cache loops): one 1024x1024 page,
+    M = 4096 memory tokens, N = 64 instances, pt 128 + 64 x (32 poly + 25 rec) greedy steps, CUDA graphs on.
+      (a) teacher-forced logits of ALL 129 sequences (pt, 64 poly, 64 rec; every position) vs the CPU oracle <= 1e-3;
+      (b) greedy ids vs the reference ids: identical, or judged near-tie flips, counted, printed and bounded;
+      (c) the same page inside a 16-page batch, decoded by 5 contexts in flight that share one set of weights, gives
+          the same ids in every context (batch / concurrency invariance at the benchmark's own configuration)."""
+    import json
+    import threading
+    from advancedliteratemachinery_b200 import NestedTensor, OmniParserB200, OmniVocab
+    from oracle import omniparser_ref as O
+    from oracle.gen_golden import CONFIG2_CASE, config2_page
+    from tests.conftest import omni_sd
+    case = CONFIG2_CASE
+    gold = np.load(os.path.join(golden_dir, 'omni_config2_page0.npz'))
+    sd = omni_sd(case['wseed'], case['pt_eos_bias'])
+    for k in list(_MODELS):
+        _MODELS.pop(k).ctx.close()
+    v = OmniVocab(pt_seq_length=case['pt_seq_length'], rec_length=case['rec_length'])
+    m = OmniParserB200(sd, v, workspace_mb=20480)
+    img, mask = config2_page(case['seed'])
+    out = m.forward_batch(NestedTensor(img, None))[0]
+    (pt, poly, rec), (probs,) = out
+    n = 64
+    assert pt.numel() == 2 * n and poly.numel() == 32 * n and tuple(rec.shape) == (1, n, 25)
+    gpt, gpoly, grec = torch.from_numpy(gold['pt']), torch.from_numpy(gold['poly']), torch.from_numpy(gold['rec'])
+
+    # ---- (a) teacher-forced logits on the REFERENCE ids: CUDA path vs CPU oracle, all sequences, all positions
+    mem, pos, kpm, _ = O.encode(img, mask, sd)
+    full = {'pt': torch.cat([v.pt_prompt(), gpt], 1),
+            'poly': torch.cat([gpt.reshape(-1, 2), torch.full((n, 1), v.poly_sos_index), gpoly.reshape(n, 32)], 1),
+            'rec': torch.cat([gpt.reshape(-1, 2), torch.full((n, 1), v.rec_sos_index), grec[0]], 1)}
+    ref_lg, our_lg, worst = {}, {}, {}
+    for kind, seq in full.items():
+        ref_lg[kind] = O.decode_logits(seq, mem[0], kpm[0], pos[0], sd, kind)
+        our_lg[kind] = m.decode_logits(0, kind, seq)
+        worst[kind] = _maxrel(our_lg[kind], ref_lg[kind])
+        assert worst[kind] < LOGIT_REL_TOL and _rel(our_lg[kind], ref_lg[kind]) < LOGIT_REL_TOL, (kind, worst[kind])
+
+    # ---- (b) greedy ids vs the reference
+    def flips_vs_reference(o):
+        (pt_, poly_, rec_), (probs_,) = o
+        assert pt_.numel() == 2 * n
+        fl = _judge_flips('pt', pt_.numpy(), gold['pt'], gold['gap_pt'], ref_lg['pt'], our_lg['pt'], 7, O.step_candidates)
+        if not fl:  # same instance set: every polygon / transcription row is comparable
+            fl += _judge_flips('poly', poly_.numpy().reshape(n, 32), gold['poly'].reshape(n, 32), gold['gap_poly'],
+                               ref_lg['poly'], our_lg['poly'], 3, O.step_candidates)
+            fl += _judge_flips('rec', rec_.numpy()[0], gold['rec'][0], gold['gap_rec'], ref_lg['rec'], our_lg['rec'], 3,
+                               O.step_candidates)
+            if np.array_equal(rec_.numpy(), gold['rec']):
+                np.testing.assert_allclose(probs_.numpy(), gold['probs'], rtol=2e-3, atol=1e-7)
+        return fl
+
+    flips = flips_vs_reference(out)
+    report = dict(logit_max_rel=worst, near_tie_flips=flips, sequences=2 * n + 1, greedy_steps=128 + n * 57,
+                  smallest_reference_gap=float(min(gold['gap_pt'].min(), gold['gap_poly'].min(), gold['gap_rec'].min())))
+    print('config-2 page parity:', json.dumps(report))
+    assert len(flips) <= MAX_NEAR_TIE_FLIPS, flips
+
+    # ---- (c) 16-page batch, 5 contexts in flight sharing one set of weights, graphs on
+    pages = torch.cat([config2_page(case['seed'] + i)[0] for i in range(16)]).pin_memory()
+    models = [m] + [OmniParserB200(None, v, workspace_mb=20480, share_from=m) for _ in range(4)]
+    results = [None] * 5
+
+    def work(j):
+        for _ in range(2):  # second round replays the captured graphs
+            results[j] = models[j].forward_batch(NestedTensor(pages, None))
+    ts = [threading.Thread(target=work, args=(j,)) for j in range(5)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert all(r is not None and len(r) == 16 for r in results)
+    for j in range(1, 5):   # the five concurrent contexts agree bit for bit on all 16 pages
+        for k in range(16):
+            for x, y in zip(results[j][k][0], results[0][k][0]):
+                assert torch.equal(x, y), f'context {j} page {k} differs from context 0'
+    # page 0 inside the batch vs the reference (the key-range split of the fused attention depends on the batch size,
+    # so "alone" and "in a batch" may round differently: each is held to the reference separately)
+    batch_flips = flips_vs_reference(results[0][0])
+    report['near_tie_flips_in_batch'] = batch_flips
+    report['batch_page0_equals_page_alone'] = all(torch.equal(x, y) for x, y in zip(results[0][0][0], out[0]))
+    print('config-2 batch parity:', json.dumps(report))
+    assert len(batch_flips) <= MAX_NEAR_TIE_FLIPS, batch_flips
+    outdir = os.path.join(os.path.dirname(os.path.dirname(golden_dir)), 'gpurun_out')
+    if os.path.isdir(outdir):
+        with open(os.path.join(outdir, 'r2_config2_parity.json'), 'w') as f:
+            json.dump(report, f)
+    for mm in models[1:]:
+        mm.ctx.close()
+    m.ctx.close()
+
+
+def test_default_vocab_runs_and_position_table_exhaustion_is_an_error():
+    """OmniVocab() defaults (pt_seq_length 1024, 7-token prompt: 1030 > the 1024-row position table): the reference runs
+    this configuration because EOS ends the loop early (transformer.py:126); it only fails if step 1018 is reached."""
+    from advancedliteratemachinery_b200 import AlmError, NestedTensor, OmniVocab
+    from oracle import omniparser_ref as O
+    from oracle.gen_golden import OMNI_CASES, omni_inputs
+    from tests.conftest import omni_sd
+    case = OMNI_CASES['eos']
+    m = model_for(case['wseed'], case['pt_eos_bias'])
+    keep = (m.vocab.pt_seq_length, m.vocab.rec_length)
+    try:
+        dv = OmniVocab()
+        assert dv.pt_seq_length == 1024
+        m.vocab.pt_seq_length, m.vocab.rec_length = dv.pt_seq_length, dv.rec_length
+        img, mask = omni_inputs(case)
+        out = m.forward_batch(NestedTensor(img, mask))[0]
+        sd = omni_sd(case['wseed'], case['pt_eos_bias'])
+        mem, pos, kpm, _ = O.encode(img, mask, sd)
+        ref = O.greedy_text_spotting(mem[0], kpm[0], pos[0], sd, dv.pt_prompt(), 1024, 25)
+        for x, y in zip(out[0], ref[0]):
+            assert torch.equal(x, y)
+    finally:
+        m.vocab.pt_seq_length, m.vocab.rec_length = keep
+    m2 = model_for(0, -30.0)   # pt_eos suppressed: the loop runs into the end of the position table
+    keep = m2.vocab.pt_seq_length
+    try:
+        m2.vocab.pt_seq_length = 1024
+        img, mask = omni_inputs(OMNI_CASES['oddlen'])
+        with pytest.raises(AlmError, match='position table'):
+            m2.forward_batch(NestedTensor(img, mask))
+    finally:
+        m2.vocab.pt_seq_length = keep
+
+
+def test_shared_weights_contexts_and_stream_ordered_device_inputs():
+    """alm_share_weights: a second context over the same device weights decodes identically, and keeps working after the
+    owner context is freed (the slabs are ref-counted).  Device inputs produced on torch's current stream right before
+    the call are ordered by alm_stream_wait inside the adapter."""
+    from advancedliteratemachinery_b200 import NestedTensor, OmniParserB200, OmniVocab
+    from tests.conftest import omni_sd
+    for k in list(_MODELS):
+        _MODELS.pop(k).ctx.close()
+    free0 = torch.cuda.mem_get_info()[0]
+    v = OmniVocab(pt_seq_length=6)
+    owner = OmniParserB200(omni_sd(0, 0.45), v, workspace_mb=4096)
+    used_one = free0 - torch.cuda.mem_get_info()[0]
+    second = OmniParserB200(None, v, workspace_mb=4096, share_from=owner)
+    g = torch.Generator().manual_seed(33)
+    host = torch.randn(2, 3, 96, 128, generator=g)
+    a = owner.forward_batch(NestedTensor(host, None))
+    # device input written by async torch work on the current stream immediately before the call
+    big = torch.randn(64, 1024, 1024, device='cuda')
+    for _ in range(8):
+        big = big @ big.transpose(1, 2) * 1e-3   # keeps the torch stream busy
+    dev = (host.pin_memory().cuda(non_blocking=True) + big.mean() * 0).contiguous()
+    b = second.forward_batch(NestedTensor(dev, None))
+    used_two = free0 - torch.cuda.mem_get_info()[0] - big.numel() * 4 * 2
+    for x, y in zip(a, b):
+        assert (x is None) == (y is None)
+        if x is not None:
+            for s, t in zip(x[0], y[0]):
+                assert torch.equal(s, t)
+    assert used_two - used_one < 0.5 * used_one, 'the second context must not hold its own copy of the weights'
+    owner.ctx.close()
+    c = second.forward_batch(NestedTensor(host, None))
+    for x, y in zip(a, c):
+        if x is not None:
+            for s, t in zip(x[0], y[0]):
+                assert torch.equal(s, t)
+    second.ctx.close()
+
+
+def test_comm_entry_points_single_rank():
+    """alm_comm_* with a one-rank NCCL communicator: id, init, weight broadcast (in place, values unchanged), gather."""
+    from advancedliteratemachinery_b200 import NestedTensor
+    m = model_for(0, 0.45)
+    m.vocab.pt_seq_length = 6
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(1, 3, 64, 96, generator=g)
+    before = m.forward_batch(NestedTensor(img, None))
+    uid = m.ctx.comm_unique_id()
+    assert len(uid) == 128
+    m.ctx.comm_init(uid, 0, 1)
+    m.ctx.broadcast_weights(0)
+    after = m.forward_batch(NestedTensor(img, None))
+    for x, y in zip(before, after):
+        assert (x is None) == (y is None)
+        if x is not None:
+            for s, t in zip(x[0], y[0]):
+                assert torch.equal(s, t)
+    from advancedliteratemachinery_b200.dist import gather_sequences
+    back = gather_sequences(after, m.vocab, ctx=m.ctx)
+    assert len(back) == 1 and (back[0] is None) == (after[0] is None)
+    if after[0] is not None:
+        for s, t in zip(after[0][0], back[0][0]):
+            assert torch.equal(s, t)
+
+
+def test_points_only_decode_equals_the_point_loop_of_the_full_decode():
+    """alm_omni_decode_points (decode_pt_seq alone, transformer.py:102-141) == the pt output of the full decode, for a
+    batch mixing an early-EOS page, an odd-length page and a page without points."""
+    from advancedliteratemachinery_b200 import NestedTensor
+    from oracle.gen_golden import OMNI_CASES, omni_inputs
+    m = model_for(0, 0.45)
+    m.vocab.pt_seq_length = 12
+    m.vocab.rec_length = 25
+    names = ['eos', 'oddlen', 'empty']
+    imgs = torch.cat([omni_inputs(OMNI_CASES[n])[0] for n in names])
+    masks = torch.cat([omni_inputs(OMNI_CASES[n])[1] for n in names])
+    outs = m.forward_batch(NestedTensor(imgs, masks))
+    m.encode(imgs, masks)
+    pts = m.decode_points()
+    assert len(pts) == 3
+    for o, (tok, prob) in zip(outs, pts):
+        if o is None:
+            assert tok.numel() == 0
+        else:
+            assert torch.equal(o[0][0].reshape(-1), tok) and prob.numel() == tok.numel()
+            assert float(prob.min()) > 0 and float(prob.max()) <= 1

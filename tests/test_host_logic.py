@@ -1,6 +1,6 @@
 """CPU checks of host-side scheduling arithmetic (no GPU).
 
-* `bench.pick_inflight`: the number of in-flight contexts for a K-step timed region.
+* `bench.py`: workload table / config object shared by both arms, decoded-character counting.
 * the run / owner arithmetic of the persistent fused cross-attention (`csrc/xattn.cu`): restated here line for
   line (integer arithmetic only) and checked for the invariants the kernel's merge protocol relies on.
 """
@@ -18,15 +18,25 @@ def _bench():
     return mod
 
 
-def test_pick_inflight_fills_rounds():
+def test_bench_workloads_and_reference_config_agree():
+    """Every BASELINE config that bench.py measures is a named workload, and the GPU arm and the reference arm print
+    the same `config` object for it (what the driver's same_config check compares)."""
     b = _bench()
-    for k in range(1, 65):
-        c = b.pick_inflight(k)
-        assert 1 <= c <= 6 and c <= k
-        if k <= 12:
-            tail = k % c
-            assert tail == 0 or tail >= c // 2, (k, c)  # short runs: never a nearly empty last round
-    assert b.pick_inflight(8) == 4 and b.pick_inflight(5) == 5 and b.pick_inflight(1) == 1
+    assert set(b.WORKLOADS) == {'omni', 'mgpstr', 'table', 'platypus'}
+    for name, w in b.WORKLOADS.items():
+        for world in (1, 2, 8):
+            c1, c2 = b.workload_config(name, world, 3), b.workload_config(name, world, 1)
+            assert c1 == c2 and c1['global_batch'] == world * w['batch'] and c1['parallelism'] == f'dp{world}'
+    assert b.WORKLOADS['omni']['pt_len'] == 2 * b.N_INST == 128 and b.WORKLOADS['table']['pt_len'] == 512
+
+
+def test_mgp_decoded_chars_counts_tokens_before_eos():
+    import torch
+    b = _bench()
+    ids = torch.zeros(3, 2, 27, dtype=torch.int32)
+    ids[0, 0, 1:6] = torch.tensor([5, 6, 7, 1, 9])   # 3 chars then [s]
+    ids[0, 1, 1:] = 4                                 # no [s]: all 26 positions count
+    assert b.mgp_decoded_chars(ids) == 3 + 26
 
 
 def _plan(npairs, nkb, num_sms, ctas_per_sm):

@@ -82,3 +82,45 @@ def test_kie_oracle_matches_reference_fixture(golden_dir):
     assert [r[1] for r in res] == gold['classes'].tolist()
     assert np.array_equal(pt_seq.numpy(), gold['pt_seq'])
     np.testing.assert_allclose(np.array([r[3] for r in res]), gold['rects'])
+
+
+@pytest.mark.parametrize('name', ['tiny', 'small', 'large', 'charstr'])
+def test_mgpstr_variant_oracle_matches_reference_fixture(name, golden_dir):
+    """tiny / small / large MGP-STR (mgp_str.py:176-230) and the char-only CHAR-STR (char_str.py:43-81): restatement vs
+    fixtures written from the reference classes."""
+    from oracle import weights as W
+    from oracle.gen_golden import MGP_VARIANT_CASES
+    case = MGP_VARIANT_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f'mgp_{name}.npz'))
+    char_only = name == 'charstr'
+    dim, depth, heads = W.MGP_VARIANTS['base' if char_only else name]
+    assert (dim, depth, heads) == tuple(gold['dims'])
+    sd = W.mgpstr_state_dict(seed=case['seed'], dim=dim, depth=depth, heads=heads, char_only=char_only)
+    g = torch.Generator().manual_seed(case['seed'])
+    img = torch.rand(2, 3, 32, 128, generator=g)
+    out = M.forward(img, sd, depth=depth, heads=heads)
+    np.testing.assert_allclose(out[1].numpy(), gold['char'], atol=3e-5, rtol=0)
+    np.testing.assert_allclose(out[0][0].numpy(), gold['char_attn'], atol=1e-6, rtol=0)
+    if not char_only:
+        for nm, lg in (('bpe', out[2]), ('wp', out[3])):
+            assert np.array_equal(lg.argmax(-1).numpy(), gold[nm + '_ids'])
+            np.testing.assert_allclose(lg.reshape(-1)[::997].numpy(), gold[nm + '_s'], atol=3e-5, rtol=0)
+
+
+def test_restated_timm_vit_matches_the_independent_hf_port(golden_dir):
+    """The pin of the timm-0.4.12 layer: oracle/mgpstr_ref.py (and with it oracle/shim/timm) against
+    HuggingFace transformers' MGP-STR port built with the reference's LayerNorm epsilons (oracle/pin_timm_hf.py), on the
+    synthetic base checkpoint and on the tiny geometry; plus the committed HF fixture."""
+    pytest.importorskip('transformers')
+    from oracle import pin_timm_hf as P
+    from oracle import weights as W
+    g = torch.Generator().manual_seed(11)
+    img = torch.rand(2, 3, 32, 128, generator=g)
+    d, out = P.cross_check(mgp_sd(0), img, W.VIT_DIM, W.VIT_DEPTH, W.VIT_HEADS)
+    assert max(d.values()) < 2e-5, d
+    gold = np.load(os.path.join(golden_dir, 'mgp_hf_b2.npz'))
+    np.testing.assert_allclose(out.logits[0].numpy(), gold['char'], atol=3e-5, rtol=0)
+    assert np.array_equal(out.logits[1].argmax(-1).numpy(), gold['bpe_ids'])
+    dim, depth, heads = W.MGP_VARIANTS['tiny']
+    d2, _ = P.cross_check(W.mgpstr_state_dict(seed=21, dim=dim, depth=depth, heads=heads), img, dim, depth, heads)
+    assert max(d2.values()) < 2e-5, d2
