@@ -214,6 +214,7 @@ struct Ctx {
   int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
   int xattn_impl = 0;  // 0 = fused flash-style cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM,
                        // 2 = fused, TMA + mbarrier pipeline (xattn_tma.cu; experimental)
+  int attn_impl = 1;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM
   int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
@@ -265,6 +266,10 @@ void window_attention(Ctx* c, const float* qkv, int C, int heads, int nWh, int n
 constexpr float WATTN_QSCALE = 0.17677669529663687f;  // 32 ** -0.5 (swin_transformer.py:130)
 void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B,
                             int shift, int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
+
+// fused dense attention for <= 272 tokens x 64-wide heads on tcgen05 (attn_tc.cu)
+void attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, long ld, int B, int T, int H, bf16* out_hi, bf16* out_lo,
+                  float* out_f32, long ldo);
 
 void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo);
 

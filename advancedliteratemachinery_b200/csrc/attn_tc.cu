@@ -1,0 +1,350 @@
+// Fused dense self-attention of the ViT blocks (MGP-STR: 257 tokens x 64-wide heads) on the 5th-gen tensor cores:
+//
+//     S = Q K^T          tcgen05.mma, operands staged by TMA into 128B-swizzled shared memory, accumulator in TMEM
+//     P = softmax(S*c)   read from TMEM (tcgen05.ld), exp2 in registers, written BACK into TMEM (tcgen05.st) as bf16
+//     O = P V            tcgen05.mma with the A operand in TMEM and V as an MN-major shared-memory operand
+//
+// Neither the scores nor the probabilities ever exist in HBM (the unfused path wrote ~5 GB of them per layer at B = 512).
+// Reference arithmetic: timm-0.4.12 Attention (restated in oracle/shim/timm/models/vision_transformer.py; called from
+// OCR/MGP-STR/modules/mgp_str.py:73-74): attn = (q @ k^T) * head_dim^-0.5; softmax; attn @ v.
+//
+// One persistent CTA per SM walks the (crop, head) items.  Per item the keys / values of the head (all T <= 272 of them)
+// are loaded once, then the ceil(T/128) query tiles run through
+//     warp 0      TMA producer (one elected lane)
+//     warp 1      tcgen05.mma issuer (one elected lane)
+//     warps 2..5  softmax + output epilogue: thread = query row (the TMEM lane its warp may access)
+// with mbarrier hand-offs: S(i+1) is issued right behind P(i) V, so it runs while the epilogue of tile i drains O.
+// TMEM map (512 columns): S [0, TK) fp32; P_hi [TK, TK + TK/2) bf16 pairs; O [TK + TK/2, +64) fp32; in split mode the low
+// halves P_lo overwrite S in place, behind the read pointer of the (single) thread that owns the row.
+//
+// NSPLIT = 3 carries q, k, v and p as (hi, lo) bf16 pairs and issues hi*hi + lo*hi + hi*lo into the same accumulator
+// (fp32-class); NSPLIT = 1 is single-pass bf16.
+#include <algorithm>
+
+#include "alm_internal.h"
+#include "ptx.cuh"
+
+namespace alm {
+
+namespace {
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TKMAX = 272;             // keys padded to a multiple of 16 (UMMA N granularity at M = 128)
+constexpr int AT_BOX = 136;               // rows of one TMA box: two boxes cover the keys, one covers a 128-row Q tile
+constexpr int AT_BOXB = AT_BOX * 128;     // 17 408 bytes, a multiple of the 1024-byte swizzle atom
+constexpr int AT_KVB = 2 * AT_BOXB;       // one K or V plane: 272 rows of 128 bytes
+constexpr int AT_QSTAGES = 2;
+
+template <int NSPLIT>
+struct AtSmem {
+  static constexpr int NP = NSPLIT == 3 ? 2 : 1;  // planes
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + NP * AT_KVB;
+  static constexpr int kQ = kV + NP * AT_KVB;
+  static constexpr int kBar = kQ + AT_QSTAGES * NP * AT_BOXB;
+  static constexpr int kTotal = kBar + 256 + 1024;  // + alignment slack
+};
+
+struct AtParams {
+  int B, T, H, D;          // crops, tokens per crop, heads, model width (H * 64)
+  int TK;                  // keys padded to 16
+  int tiles;               // ceil(T / 128)
+  long items;              // B * H
+  float scale_log2e;       // head_dim^-0.5 * log2(e)
+  bf16* out_hi;
+  bf16* out_lo;
+  float* out_f32;
+  long ldo;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const AtParams p) {
+  using L = AtSmem<NSPLIT>;
+  constexpr int NP = L::NP;
+  extern __shared__ uint8_t at_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;    // [2]
+  uint64_t* q_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TK = p.TK;
+  const uint32_t S_COL = 0, P_COL = TK, O_COL = TK + TK / 2, PLO_COL = 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_hi);
+    if (NSPLIT == 3) ptx::prefetch_tmap(&tm_lo);
+    ptx::mbar_init(kv_full, 1);
+    ptx::mbar_init(kv_empty, 1);
+    for (int s = 0; s < AT_QSTAGES; ++s) {
+      ptx::mbar_init(&q_full[s], 1);
+      ptx::mbar_init(&q_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 4);   // one arrival per softmax warp
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(o_empty, 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================================= TMA producer
+    uint32_t kv_phase = 0, q_phase = 0;
+    int qs = 0;
+    for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const int b = static_cast<int>(it / p.H), h = static_cast<int>(it % p.H);
+      const int row0 = b * p.T;
+      ptx::mbar_wait(kv_empty, kv_phase ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(kv_full, 4 * NP * AT_BOXB);
+        for (int pl = 0; pl < NP; ++pl) {
+          const void* tm = pl ? static_cast<const void*>(&tm_lo) : static_cast<const void*>(&tm_hi);
+          for (int half = 0; half < 2; ++half) {
+            ptx::tma_load_2d(smem + L::kK + pl * AT_KVB + half * AT_BOXB, tm, kv_full, p.D + h * 64, row0 + half * AT_BOX);
+            ptx::tma_load_2d(smem + L::kV + pl * AT_KVB + half * AT_BOXB, tm, kv_full, 2 * p.D + h * 64, row0 + half * AT_BOX);
+          }
+        }
+      }
+      __syncwarp();
+      kv_phase ^= 1;
+      for (int i = 0; i < p.tiles; ++i) {
+        ptx::mbar_wait(&q_empty[qs], q_phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&q_full[qs], NP * AT_BOXB);
+          for (int pl = 0; pl < NP; ++pl)
+            ptx::tma_load_2d(smem + L::kQ + (qs * NP + pl) * AT_BOXB, pl ? static_cast<const void*>(&tm_lo) : static_cast<const void*>(&tm_hi),
+                             &q_full[qs], h * 64, row0 + i * 128);
+        }
+        __syncwarp();
+        if (++qs == AT_QSTAGES) { qs = 0; q_phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================================= MMA issuer
+    // instruction descriptors: D = f32, A = B = bf16; N >> 3 at [17,23), M >> 4 at [24,29); bit 16 = B is MN-major
+    const int n1 = TK > 256 ? 256 : TK, n2 = TK - n1;
+    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 4) << 24);
+    const uint32_t idesc_s1 = idesc_base | (uint32_t(n1 >> 3) << 17);
+    const uint32_t idesc_s2 = idesc_base | (uint32_t(n2 >> 3) << 17);
+    const uint32_t idesc_pv = idesc_base | (1u << 16) | (uint32_t(64 >> 3) << 17);
+    uint32_t kv_phase = 0, q_phase = 0, p_phase = 0, oe_phase = 0;
+    int qs = 0;
+    const uint32_t k_base = ptx::smem_u32(smem + L::kK), v_base = ptx::smem_u32(smem + L::kV);
+    for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      ptx::mbar_wait(kv_full, kv_phase);
+      kv_phase ^= 1;
+      for (int i = 0; i < p.tiles; ++i) {
+        ptx::mbar_wait(&q_full[qs], q_phase);
+        ptx::tc_fence_after();
+        const uint32_t q_base = ptx::smem_u32(smem + L::kQ + qs * NP * AT_BOXB);
+        if (ptx::elect_one()) {
+          // ---- S = Q K^T : passes (q_hi, k_hi), (q_lo, k_hi), (q_hi, k_lo)
+#pragma unroll
+          for (int pass = 0; pass < NSPLIT; ++pass) {
+            const uint32_t qa = q_base + (pass == 1 ? AT_BOXB : 0);
+            const uint32_t kb = k_base + (pass == 2 ? AT_KVB : 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = ptx::make_kmajor_sw128_desc(qa + k * 32);
+              ptx::umma_bf16(tmem + S_COL, da, ptx::make_kmajor_sw128_desc(kb + k * 32), idesc_s1, (pass | k) != 0);
+              if (n2 > 0)
+                ptx::umma_bf16(tmem + S_COL + n1, da, ptx::make_kmajor_sw128_desc(kb + n1 * 128 + k * 32), idesc_s2,
+                               (pass | k) != 0);
+            }
+          }
+          ptx::umma_commit(&q_empty[qs]);
+          ptx::umma_commit(s_full);
+        }
+        __syncwarp();
+        if (++qs == AT_QSTAGES) { qs = 0; q_phase ^= 1; }
+        // ---- O = P V once the softmax warps have written P (and the previous O has been drained)
+        ptx::mbar_wait(p_full, p_phase);
+        p_phase ^= 1;
+        ptx::mbar_wait(o_empty, oe_phase ^ 1);
+        oe_phase ^= 1;
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const int ksteps = TK / 16;
+#pragma unroll
+          for (int pass = 0; pass < NSPLIT; ++pass) {
+            const uint32_t pa = tmem + (pass == 1 ? PLO_COL : P_COL);
+            const uint32_t vb = v_base + (pass == 2 ? AT_KVB : 0);
+            for (int j = 0; j < ksteps; ++j)
+              ptx::umma_bf16_ts(tmem + O_COL, pa + j * 8, ptx::make_kmajor_sw128_desc(vb + j * 2048), idesc_pv, (pass | j) != 0);
+          }
+          ptx::umma_commit(o_full);
+          if (i == p.tiles - 1) ptx::umma_commit(kv_empty);  // K / V of this item are free once these MMAs retire
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================================= softmax + epilogue warps
+    const int quarter = warp & 3;  // the TMEM lanes [32*quarter, +32) this warp may access
+    const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
+    uint32_t s_phase = 0, o_phase = 0;
+    for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const int b = static_cast<int>(it / p.H), h = static_cast<int>(it % p.H);
+      for (int i = 0; i < p.tiles; ++i) {
+        const int row = i * 128 + quarter * 32 + lane;
+        const bool warp_live = i * 128 + quarter * 32 < p.T;
+        ptx::mbar_wait(s_full, s_phase);
+        s_phase ^= 1;
+        ptx::tc_fence_after();
+        float l = 1.0f;
+        if (warp_live) {
+          // pass 1: row maximum over the live keys
+          float m = -INFINITY;
+          for (int c0 = 0; c0 < TK; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x16(lane_addr + S_COL + c0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+          // pass 2: p = 2^((s - m) * c); row sum; bf16 (hi, lo) pairs back into tensor memory
+          const float mc = m * p.scale_log2e;
+          l = 0.f;
+          for (int c0 = 0; c0 < TK; c0 += 16) {
+            uint32_t v[16], ph[8], pl[8];
+            ptx::tmem_ld_32x16(lane_addr + S_COL + c0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float e0 = c0 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc)) : 0.f;
+              float e1 = c0 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc)) : 0.f;
+              l += e0 + e1;
+              bf16 h0, l0, h1, l1;
+              split_bf16(e0, h0, l0);
+              split_bf16(e1, h1, l1);
+              ph[j >> 1] = pack_bf16(h0, h1);
+              pl[j >> 1] = pack_bf16(l0, l1);
+            }
+            ptx::tmem_st_32x8(lane_addr + P_COL + (c0 >> 1), ph);
+            if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + PLO_COL + (c0 >> 1), pl);  // behind this thread's read pointer
+          }
+          ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_full);
+        // ---- epilogue: O / l -> split bf16 planes (operand of the projection GEMM), token-major [B*T, D]
+        ptx::mbar_wait(o_full, o_phase);
+        o_phase ^= 1;
+        ptx::tc_fence_after();
+        if (warp_live) {
+          const float inv = 1.0f / l;
+          const long orow = (static_cast<long>(b) * p.T + row) * p.ldo + h * 64;
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x16(lane_addr + O_COL + c0, v);
+            ptx::tmem_ld_wait();
+            if (row < p.T) {
+              uint32_t hh[8], ll[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float x0 = __uint_as_float(v[j]) * inv, x1 = __uint_as_float(v[j + 1]) * inv;
+                bf16 h0, l0, h1, l1;
+                split_bf16(x0, h0, l0);
+                split_bf16(x1, h1, l1);
+                hh[j >> 1] = pack_bf16(h0, h1);
+                ll[j >> 1] = pack_bf16(l0, l1);
+                if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + orow + c0 + j) = make_float2(x0, x1);
+              }
+              if (p.out_hi) {
+                *reinterpret_cast<uint4*>(p.out_hi + orow + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                *reinterpret_cast<uint4*>(p.out_hi + orow + c0 + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+              }
+              if (p.out_lo) {
+                *reinterpret_cast<uint4*>(p.out_lo + orow + c0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + orow + c0 + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(o_empty);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+CUtensorMap qkv_map(Ctx* c, const bf16* base, long rows, long ld) {
+  CUtensorMap tm;
+  ALM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0, ALM_ERR_INVALID, "attention operand alignment");
+  cuuint64_t dims[2] = {cuuint64_t(ld), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {64, cuuint32_t(AT_BOX)};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw AlmError{ALM_ERR_CUDA, "cuTensorMapEncodeTiled (attention qkv plane) failed with CUresult " + std::to_string(int(r))};
+  return tm;
+}
+
+}  // namespace
+
+// qkv: token-major [B*T, 3*D] split bf16 planes (q | k | v blocks of D columns, head h at columns h*64 of its block), as
+// the fused qkv GEMM writes them.  out: [B*T, D] split planes (and / or fp32).  T <= 272, head width 64.
+void attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, long ld, int B, int T, int H, bf16* out_hi, bf16* out_lo,
+                  float* out_f32, long ldo) {
+  ALM_REQUIRE(T >= 1 && T <= AT_TKMAX && H >= 1 && B >= 1, ALM_ERR_UNSUPPORTED, "attention_tc: at most 272 tokens per sequence");
+  ALM_REQUIRE(ld >= 3L * H * 64 && ldo % 8 == 0, ALM_ERR_INVALID, "attention_tc: leading dimensions");
+  const bool three = c->nsplit == 3;
+  ALM_REQUIRE(!three || qkv_lo, ALM_ERR_INVALID, "attention_tc: split mode needs the lo plane");
+  AtParams p;
+  p.B = B; p.T = T; p.H = H; p.D = H * 64;
+  p.TK = (T + 15) & ~15;
+  if (p.TK < 32) p.TK = 32;
+  p.tiles = (T + 127) / 128;
+  p.items = static_cast<long>(B) * H;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32; p.ldo = ldo;
+  const long rows = static_cast<long>(B) * T;
+  const CUtensorMap th = qkv_map(c, qkv_hi, rows, ld);
+  const CUtensorMap tl = three ? qkv_map(c, qkv_lo, rows, ld) : th;
+  const int grid = static_cast<int>(std::min<long>(p.items, c->num_sms));
+  static DeviceOnce attr;
+  if (attr.need()) {
+    ALM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtSmem<3>::kTotal));
+    ALM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtSmem<1>::kTotal));
+    attr.mark();
+  }
+  if (three) attention_tc_kernel<3><<<grid, AT_THREADS, AtSmem<3>::kTotal, c->stream>>>(th, tl, p);
+  else attention_tc_kernel<1><<<grid, AT_THREADS, AtSmem<1>::kTotal, c->stream>>>(th, tl, p);
+  count_launch(c);
+  check_launch("attention_tc");
+}
+
+}  // namespace alm

@@ -186,6 +186,9 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "xattn_impl") {
       ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "xattn_impl must be 0, 1 or 2");
       h->c.xattn_impl = static_cast<int>(value);
+    } else if (k == "attn_impl") {
+      ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "attn_impl must be 0 or 1");
+      h->c.attn_impl = static_cast<int>(value);
     } else if (k == "wattn_impl") {
       h->c.wattn_impl = value ? 1 : 0;
     } else if (k == "enc_grid_cap") {
@@ -702,6 +705,23 @@ int alm_op_linear(alm_ctx* h, const float* A, const float* W, const float* bias,
     e.out_f32 = C; e.ldo = N; e.obs0 = static_cast<long>(M) * N;
     e.bias = bias; e.bias_mode = bias ? BIAS_COL : BIAS_NONE; e.act = act;
     gemm(c, a, b, e);
+    ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int alm_op_attention(alm_ctx* h, const float* qkv, float* out, int B, int T, int H) {
+  return guarded(h, [&] {
+    ALM_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, ALM_ERR_INVALID, "alm_op_attention arguments");
+    ALM_REQUIRE(is_device_ptr(qkv) && is_device_ptr(out), ALM_ERR_INVALID, "device pointers required");
+    Ctx* c = &h->c;
+    c->ensure_ws();
+    ArenaScope arena_scope(c->ws);
+    const long R = static_cast<long>(B) * T;
+    const int D = H * 64;
+    bf16* hi = c->ws.get<bf16>(static_cast<size_t>(R) * 3 * D);
+    bf16* lo = c->ws.get<bf16>(static_cast<size_t>(R) * 3 * D);
+    split_rows(c, qkv, 3 * D, R, 3 * D, hi, lo, 3 * D);
+    attention_tc(c, hi, lo, 3L * D, B, T, H, nullptr, nullptr, out, D);
     ALM_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   });
 }

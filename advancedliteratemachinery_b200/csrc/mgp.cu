@@ -26,7 +26,8 @@ struct MgpLN {
 };
 struct MgpBlock {
   MgpLN n1, n2;
-  MgpLin qk, v, proj, fc1, fc2;
+  MgpLin qkv, proj, fc1, fc2;  // qkv = the packed [3D, D] projection (rows q | k | v), as in the checkpoint
+  MgpLin qk, v;                // row views [0, 2D) and [2D, 3D) of qkv for the unfused attention path
 };
 struct MgpA3 {
   MgpLN token_norm, norm;
@@ -186,10 +187,12 @@ void mgp_load(Ctx* c, const std::map<std::string, HostTensor>& tin) {
     const HostTensor& qb = need(t, p + "attn.qkv.bias");
     ALM_REQUIRE(qw.numel() == static_cast<size_t>(3) * D * D && static_cast<int>(qb.numel()) == 3 * D, ALM_ERR_INVALID,
                 "qkv shape mismatch at " + p);
-    w.qk.w = upload_split(c, qw.f32.data(), 2 * D, D, 0);
-    w.qk.b = upload_f32(c, qb.f32.data(), 2 * D);
-    w.v.w = upload_split(c, qw.f32.data() + static_cast<size_t>(2) * D * D, D, D, 0);
-    w.v.b = upload_f32(c, qb.f32.data() + 2 * D, D);
+    w.qkv.w = upload_split(c, qw.f32.data(), 3 * D, D, 0);
+    w.qkv.b = upload_f32(c, qb.f32.data(), 3 * D);
+    w.qk = w.qkv; w.qk.w.N = 2 * D;
+    w.v = w.qkv; w.v.w.N = D;
+    w.v.w.hi += static_cast<size_t>(2) * D * w.qkv.w.ld; w.v.w.lo += static_cast<size_t>(2) * D * w.qkv.w.ld;
+    w.v.b += 2 * D;
     w.proj = ld_lin(c, t, p + "attn.proj", D, D);
     w.fc1 = ld_lin(c, t, p + "mlp.fc1", 4 * D, D);
     w.fc2 = ld_lin(c, t, p + "mlp.fc2", D, 4 * D);
@@ -251,17 +254,29 @@ void mgp_forward(Ctx* c, const float* img, int B, float* attn_out, float* char_l
     gemm(c, opnd(a.hi, a.lo, B * NPATCH, 64, 64), m->patch.w.op(), e);
     ws.release(mk);
   }
+  const bool fused_attn = c->attn_impl == 0;
   SB ln = sb(c, R * D);
-  SB qk = sb(c, R * 2 * D);
-  SB vt = sb(c, static_cast<size_t>(B) * D * TP);
-  float* S = ws.get<float>(static_cast<size_t>(B) * H * T * TP);
-  SB P = sb(c, static_cast<size_t>(B) * H * T * TP);
+  SB qk{nullptr, nullptr}, vt{nullptr, nullptr}, P{nullptr, nullptr}, qkv{nullptr, nullptr};
+  float* S = nullptr;
+  if (fused_attn) {
+    qkv = sb(c, R * 3 * D);
+  } else {
+    qk = sb(c, R * 2 * D);
+    vt = sb(c, static_cast<size_t>(B) * D * TP);
+    S = ws.get<float>(static_cast<size_t>(B) * H * T * TP);
+    P = sb(c, static_cast<size_t>(B) * H * T * TP);
+  }
   SB o = sb(c, R * D);
   SB hid = sb(c, R * 4 * D);
   for (int b = 0; b < m->depth; ++b) {
     const MgpBlock& w = m->blocks[b];
     gather_ln(c, x, D, nullptr, 1, D, R, w.n1.g, w.n1.b, 1e-6f, false, nullptr, 0, nullptr, 0, ln.hi, ln.lo, D, nullptr,
               nullptr);
+    if (fused_attn) {
+      // one packed q|k|v projection, then scores + softmax + P.V on tcgen05 with S and P in tensor memory (attn_tc.cu)
+      lin(c, ln, R, w.qkv, ACT_NONE, nullptr, &qkv, nullptr);
+      attention_tc(c, qkv.hi, qkv.lo, 3L * D, B, T, H, o.hi, o.lo, nullptr, D);
+    } else {
     lin(c, ln, R, w.qk, ACT_NONE, nullptr, &qk, nullptr);
     {  // V^T[b, f, t] = Wv ln_b^T + bv  (feature-major: P.V becomes a K-major GEMM)
       Operand bop = opnd(ln.hi, ln.lo, T, D, D);
@@ -291,6 +306,7 @@ void mgp_forward(Ctx* c, const float* img, int B, float* attn_out, float* char_l
       e.out_hi = o.hi; e.out_lo = o.lo; e.ldo = D; e.obs0 = 64; e.obs1 = static_cast<long>(T) * D;
       gemm(c, p, v, e);
     }
+    }  // unfused attention
     lin(c, o, R, w.proj, ACT_NONE, x, nullptr, x);
     gather_ln(c, x, D, nullptr, 1, D, R, w.n2.g, w.n2.b, 1e-6f, false, nullptr, 0, nullptr, 0, ln.hi, ln.lo, D, nullptr,
               nullptr);

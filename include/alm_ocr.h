@@ -80,6 +80,8 @@ ALM_API const char* alm_version(void);
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
  *          "trace_gemm" (capacity; see alm_trace_read), "trace_detail" (see alm_bench_gemm_ex),
+ *          "attn_impl" (ViT attention of MGP-STR: 0 = fused tcgen05 kernel, scores / probabilities in tensor memory;
+ *          1 = score GEMM + softmax + P.V GEMM, the A/B reference),
  *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
  *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
  *          streams / in-flight batches can share the GPU),
@@ -244,6 +246,10 @@ ALM_API int alm_mgpstr_forward(alm_ctx* ctx, const float* img, int B, float* att
  * operand split + tcgen05 kernel as the model graphs.  batch > 1: contiguous batches of A, W and C. */
 ALM_API int alm_op_linear(alm_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                   int act, int batch);
+/* softmax((q k^T) * 64^-0.5) v for B sequences of T <= 272 tokens and H heads of width 64: qkv f32 [B*T, 3*H*64] (q | k | v
+ * column blocks, head h at columns h*64 of its block: the layout of timm's packed qkv Linear), out f32 [B*T, H*64].
+ * Runs the fused tcgen05 kernel of the ViT blocks (scores and probabilities stay in tensor memory). */
+ALM_API int alm_op_attention(alm_ctx* ctx, const float* qkv, float* out, int B, int T, int H);
 ALM_API int alm_op_layernorm(alm_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps, float* y,
                      long rows, int C);
 /* Swin W-MSA core on an already windowed qkv tensor [B*nWh*nWw*49, 3C] (swin_transformer.py:127-148). */

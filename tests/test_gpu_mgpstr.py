@@ -131,3 +131,51 @@ def test_config3_batch_512_rows_equal_small_batches_and_the_oracle(model):
         assert flips < 0.25
     finally:
         model.ctx.set_option('nsplit', 3)
+
+
+@pytest.mark.parametrize('B,T,H', [(2, 257, 3), (1, 50, 1), (3, 130, 2), (1, 272, 1), (40, 257, 12)])
+def test_fused_tcgen05_attention_matches_fp64(B, T, H):
+    """csrc/attn_tc.cu (S and P in tensor memory) against softmax((q k^T) * 64^-0.5) v in fp64: 257 tokens (three query
+    tiles, 272 padded keys = a 256-wide plus a 16-wide MMA), short and ragged sequences, the 272-token maximum, and
+    more items than SMs (persistent loop, K/V buffer reuse)."""
+    from advancedliteratemachinery_b200 import _lib
+    ctx = _lib.Context(0)
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + T + H)
+        D = H * 64
+        qkv = torch.randn(B * T, 3 * D, generator=g)
+        qkv[:, :D] *= 1.5   # sharper softmax than unit-variance scores
+        q, k, v = qkv.double().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+        ref = (((q @ k.transpose(-2, -1)) * 0.125).softmax(-1) @ v).transpose(1, 2).reshape(B * T, D)
+        qd = qkv.cuda()
+        for nsplit, tol in ((3, 3e-5), (1, 2e-2)):
+            ctx.set_option('nsplit', nsplit)
+            out = torch.full((B * T, D), float('nan'), device='cuda')
+            ctx.check(ctx.lib.alm_op_attention(ctx.h, qd.data_ptr(), out.data_ptr(), B, T, H))
+            err = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
+            assert err < tol, (nsplit, err)
+    finally:
+        ctx.close()
+
+
+def test_fused_attention_model_path_matches_fixture_and_unfused_path(golden_dir):
+    """MGP-STR forward with attn_impl 0 (fused tcgen05 attention + packed qkv GEMM) vs the reference fixture and vs the
+    unfused path (attn_impl 1) on the same weights."""
+    from advancedliteratemachinery_b200 import MGPSTRB200
+    from oracle.gen_golden import MGP_CASES
+    from tests.conftest import mgp_sd
+    gold = np.load(os.path.join(golden_dir, 'mgp_b3.npz'))
+    g = torch.Generator().manual_seed(MGP_CASES['b3']['seed'])
+    img = torch.rand(3, 3, 32, 128, generator=g)
+    m = MGPSTRB200(mgp_sd(0))
+    try:
+        outs = {}
+        for impl in (0, 1):
+            m.ctx.set_option('attn_impl', impl)
+            outs[impl] = m(img, is_eval=True)
+            assert _maxrel(outs[impl][1], torch.from_numpy(gold['char'])) < 1e-3, impl
+            assert np.array_equal(m.last_ids[1].to(torch.int64).numpy(), gold['bpe_ids']), impl
+            assert np.array_equal(m.last_ids[2].to(torch.int64).numpy(), gold['wp_ids']), impl
+        assert _maxrel(outs[0][1], outs[1][1]) < 1e-4
+    finally:
+        m.ctx.close()
