@@ -214,8 +214,10 @@ struct Ctx {
   int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
   int xattn_impl = 0;  // 0 = fused flash-style cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM,
                        // 2 = fused, TMA + mbarrier pipeline (xattn_tma.cu; experimental)
-  int attn_impl = 1;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM
-  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel
+  int fuse_ln_gemv = 1;  // point loop: 1 = the pre-LayerNorms run inside the following GEMV (13 fewer dependent launches per token)
+  int kv_decoders = 3;  // number of decoders (pt, poly, rec order) whose cross-attention K/V caches alm_omni_encode fills
+  int attn_impl = 0;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM
+  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel, 2 = tcgen05 + TMA (wattn_tc.cu)
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
   struct GemmRec { cudaEvent_t a, b; double flops; };
@@ -255,7 +257,9 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
                float* out2_f32 = nullptr);
 
 void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, const float* W, const float* bias,
-               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act);
+               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act,
+               const float* ln_g = nullptr, const float* ln_b = nullptr, float ln_eps = 0.f, const float* pos = nullptr,
+               int pos_split = 0);
 
 void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp, bf16* hi, bf16* lo);
 
@@ -270,6 +274,10 @@ void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int 
 // fused dense attention for <= 272 tokens x 64-wide heads on tcgen05 (attn_tc.cu)
 void attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, long ld, int B, int T, int H, bf16* out_hi, bf16* out_lo,
                   float* out_f32, long ldo);
+
+// the same on tcgen05 with TMA-staged window tiles, two windows per M = 128 tile (wattn_tc.cu)
+void window_attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B, int shift,
+                         int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
 
 void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo);
 

@@ -186,11 +186,17 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "xattn_impl") {
       ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "xattn_impl must be 0, 1 or 2");
       h->c.xattn_impl = static_cast<int>(value);
+    } else if (k == "fuse_ln_gemv") {
+      h->c.fuse_ln_gemv = value ? 1 : 0;
+    } else if (k == "kv_decoders") {
+      ALM_REQUIRE(value >= 1 && value <= 3, ALM_ERR_INVALID, "kv_decoders must be 1..3");
+      h->c.kv_decoders = static_cast<int>(value);
     } else if (k == "attn_impl") {
       ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "attn_impl must be 0 or 1");
       h->c.attn_impl = static_cast<int>(value);
     } else if (k == "wattn_impl") {
-      h->c.wattn_impl = value ? 1 : 0;
+      ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "wattn_impl must be 0, 1 or 2");
+      h->c.wattn_impl = static_cast<int>(value);
     } else if (k == "enc_grid_cap") {
       h->c.enc_grid_cap = static_cast<int>(value);
     } else if (k == "dec_grid_cap") {

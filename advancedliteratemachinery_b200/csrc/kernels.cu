@@ -461,11 +461,17 @@ softmax_rows_kernel(const float* __restrict__ s, long lds, int n, const uint8_t*
 // activation rows come from L1; a tensor-core tile would be > 90 % padding here and the op is latency-bound anyway.
 // Weights stay exact fp32, so this path is closer to the reference than the split-bf16 GEMM.
 // ---------------------------------------------------------------------------------------------
+// Optional fused pre-LayerNorm (ln_g != nullptr, K == 512 == the row width): the staged rows are the raw residual stream;
+// every CTA normalises its private copy in shared memory (16 x 512 values: far cheaper than one more dependent launch in
+// the latency-bound point loop) with exactly the arithmetic and summation order of gather_ln_kernel<4>, then adds the
+// query position embedding `pos` for the output columns below pos_split (q | k of the packed self-attention projection;
+// everything for the cross-attention query).
 template <int MR, int NW>  // MR = row capacity (8/16/32), NW = K / 128 float4 slices of the weight row per lane
 __global__ void __launch_bounds__(128)
 gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int n_split, long ldx,
                  const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ resid, long ldr,
-                 float* __restrict__ out, long ldo, int M, int N, int K, int act) {
+                 float* __restrict__ out, long ldo, int M, int N, int K, int act, const float* __restrict__ ln_g,
+                 const float* __restrict__ ln_b, float ln_eps, const float* __restrict__ pos, int pos_split) {
   // activation rows, staged in K-chunks of <= 512 floats (double-buffered when K > 512): at most 64 KB for 16 rows,
   // so this kernel co-resides with the HBM-bound attention CTAs of the other in-flight decode streams
   extern __shared__ __align__(16) float sx[];
@@ -513,6 +519,44 @@ gemv_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, int 
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (NC == 1 && ln_g != nullptr) {  // fused LayerNorm (+ pos) on the staged rows: warp w normalises rows w, w+4, ...
+      const bool add_pos = pos != nullptr && blockIdx.x * 4 < pos_split;
+      for (int m = threadIdx.x >> 5; m < M; m += 4) {
+        float* row = sx + m * KC;
+        float4 v[4];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = *reinterpret_cast<const float4*>(row + 4 * (lane + 32 * j));
+          s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / 512);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = v[j].x - mean, b2 = v[j].y - mean, c2 = v[j].z - mean, d = v[j].w - mean;
+          q += (a * a + b2 * b2) + (c2 * c2 + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512) + ln_eps);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 4 * (lane + 32 * j);
+          const float4 g = *reinterpret_cast<const float4*>(ln_g + e);
+          const float4 bb = *reinterpret_cast<const float4*>(ln_b + e);
+          float4 y;
+          y.x = (v[j].x - mean) * rstd * g.x + bb.x;
+          y.y = (v[j].y - mean) * rstd * g.y + bb.y;
+          y.z = (v[j].z - mean) * rstd * g.z + bb.z;
+          y.w = (v[j].w - mean) * rstd * g.w + bb.w;
+          if (add_pos) {
+            const float4 pp = *reinterpret_cast<const float4*>(pos + e);
+            y.x += pp.x; y.y += pp.y; y.z += pp.z; y.w += pp.w;
+          }
+          *reinterpret_cast<float4*>(row + e) = y;
+        }
+      }
+      __syncthreads();
+    }
     const float* xs = sx + static_cast<long>(c & 1) * M * KC;
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
@@ -594,6 +638,10 @@ void im2col_patch4(Ctx* c, const float* img, int B, int H, int W, int Hp, int Wp
 void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B,
                             int shift, int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32) {
   ALM_REQUIRE(C == heads * HD, ALM_ERR_UNSUPPORTED, "window_attention: head_dim must be 32");
+  if (c->wattn_impl == 2) {  // tcgen05 + TMA kernel (wattn_tc.cu)
+    window_attention_tc(c, qkv_hi, qkv_lo, C, heads, nWh, nWw, B, shift, Hp, Wp, bias_dense, out_hi, out_lo, out_f32);
+    return;
+  }
   dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
   window_attention_split_kernel<<<grid, 128, 0, c->stream>>>(qkv_hi, qkv_lo, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi,
                                                              out_lo, out_f32);
@@ -649,8 +697,10 @@ void softmax_rows(Ctx* c, const float* s, long lds, long rows, int n, const uint
 
 namespace alm {
 void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, const float* W, const float* bias,
-               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act) {
+               const float* resid, long ldr, float* out, long ldo, int M, int N, int K, int act, const float* ln_g,
+               const float* ln_b, float ln_eps, const float* pos, int pos_split) {
   if (c->skipped(2)) return;
+  ALM_REQUIRE(ln_g == nullptr || (K == 512 && ln_b != nullptr), ALM_ERR_INVALID, "gemv_rows: fused LayerNorm needs K == 512");
   ALM_REQUIRE(M >= 1 && M <= 32 && K % 4 == 0 && ldx % 4 == 0 && K <= 2048 && n_split % 4 == 0 &&
                   (K <= 512 || K % 512 == 0),
               ALM_ERR_INVALID, "gemv_rows: M <= 32, K % 4 == 0, K <= 512 or a multiple of 512 up to 2048");
@@ -666,7 +716,8 @@ void gemv_rows(Ctx* c, const float* x, const float* x2, int n_split, long ldx, c
       attr.mark();                                                                                                 \
     }                                                                                                              \
     gemv_rows_kernel<MRV, NWV><<<grid, 128, dyn, c->stream>>>(x, x2 ? x2 : x, n_split, ldx, W, bias, resid, ldr,   \
-                                                              out, ldo, M, N, K, act);                            \
+                                                              out, ldo, M, N, K, act, ln_g, ln_b, ln_eps, pos,    \
+                                                              pos_split);                                         \
   } while (0)
   const int nw = K <= 512 ? 4 : 16;
   if (M <= 8) { if (nw == 4) ALM_GEMV(8, 4); else ALM_GEMV(8, 16); }

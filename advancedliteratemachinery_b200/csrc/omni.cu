@@ -383,7 +383,7 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     Operand a = act_op(memp.hi, memp.lo, m->M, 512, 512);
     a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
     Operand w = m->ca_k_all.w.op();
-    w.rows = 64; w.nb0 = 96; w.bs0 = static_cast<long>(64) * 512;
+    w.rows = 64; w.nb0 = 32 * c->kv_decoders; w.bs0 = static_cast<long>(64) * 512;  // (decoder, layer, head) slices
     Epilogue e;
     e.out_hi = m->kc_hi; e.out_lo = m->kc_lo; e.ldo = 64;
     e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
@@ -395,7 +395,7 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     Operand a = act_op(mem.hi, mem.lo, m->M, 512, 512);
     a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
     Operand w = m->ca_v_all.w.op();
-    w.rows = 64; w.nb0 = 96; w.bs0 = static_cast<long>(64) * 512;
+    w.rows = 64; w.nb0 = 32 * c->kv_decoders; w.bs0 = static_cast<long>(64) * 512;
     Epilogue e;
     e.out_hi = m->vc_hi; e.out_lo = m->vc_lo; e.ldo = 64;
     e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
@@ -412,6 +412,7 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
   }
   ws.release(m->ws_mark);
   m->encoded = true;
+  m->kv_decoders = c->kv_decoders;
   ALM_CHECK_CUDA(cudaEventRecord(c->ev_t[1], c->stream));
   c->timing_valid[0] = true;
 }
@@ -522,6 +523,32 @@ void decoder_step(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens,
       gemv_rows(c, x, nullptr, 1 << 30, K, w.wf, w.b, resid, w.w.N, out, w.w.N, S, w.w.N, K, act);
     };
     c->skip_scope = true;  // (timing experiments: alm_set_option debug_skip drops kernel classes inside the layers)
+    if (c->fuse_ln_gemv && u.fused_xattn) {
+      // same arithmetic, 13 fewer dependent launches per token: every pre-LayerNorm (+ query position) is applied by the
+      // GEMV that consumes it, on its own staged copy of the rows
+      auto lnlin = [&](const LNW& n, const float* pos, int pos_split, const float* W_, const float* b_, int N_, int act,
+                       float* out, long ldo) {
+        gemv_rows(c, u.x, nullptr, 1 << 30, 512, W_, b_, nullptr, 0, out, ldo, S, N_, 512, act, n.g, n.b, 1e-5f, pos, pos_split);
+      };
+      for (int l = 0; l < 4; ++l) {
+        const DecLayerW& w = m->dec[d][l];
+        const long dl = static_cast<long>(d) * 4 + l;
+        lnlin(w.n1, qpos, 1024, w.sa_qkv_f, w.sa_qkv_b, 1536, ACT_NONE, u.qkv, 1536);   // q | k from LN(x)+pos, v from LN(x)
+        self_attn_step(c, u.qkv, u.qkv + 1024, u.kc[l], u.vc[l], S, u.tpos, u.Tmax, nullptr, nullptr, u.attf, 1536, 1536);
+        lin(u.attf, 512, w.sa_out, ACT_NONE, u.x, u.x);
+        lnlin(w.n2, qpos, 1 << 30, w.ca_q.wf, w.ca_q.b, 512, ACT_NONE, u.qf, 512);
+        fused_xattn(c, m, u, nullptr, nullptr, u.qf, img0, nimg, 1, dl, nullptr, nullptr, u.of);
+        lin(u.of, 512, w.ca_out, ACT_NONE, u.x, u.x);
+        lnlin(w.n3, nullptr, 0, w.l1.wf, w.l1.b, 2048, ACT_RELU, u.hidf, 2048);
+        lin(u.hidf, 2048, w.l2, ACT_NONE, u.x, u.x);
+      }
+      c->skip_scope = false;
+      if (!want_logits) return;
+      lnlin(m->dec_norm[d], nullptr, 0, m->head[d][0].wf, m->head[d][0].b, 512, ACT_RELU, u.h0f, 512);
+      lin(u.h0f, 512, m->head[d][1], ACT_RELU, u.h1f, nullptr);
+      lin(u.h1f, 512, m->head[d][2], ACT_NONE, u.logits, nullptr);
+      return;
+    }
     for (int l = 0; l < 4; ++l) {
       const DecLayerW& w = m->dec[d][l];
       const long dl = static_cast<long>(d) * 4 + l;
@@ -673,7 +700,7 @@ void run_steps(Ctx* c, OmniModel* m, int d, DecodeBufs& u, const int* tokens, in
                            reinterpret_cast<long>(u.x), reinterpret_cast<long>(tokens), tstride,
                            reinterpret_cast<long>(h.probs), reinterpret_cast<long>(h.finished), h.n_prompt_m1,
                            reinterpret_cast<long>(m->kc_hi), reinterpret_cast<long>(u.kc[3]), h.cfg.pt_eos, h.cfg.num_bins,
-                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl, c->gemm_grid_cap, c->debug_skip, c->xattn_ctas_per_sm, c->sattn_wide, c->xattn_wg};
+                           h.cfg.rec_eos, h.cfg.recog_pad, reinterpret_cast<long>(c->trace_buf), h.nsoft, h.cfg.vie, c->xattn_impl, c->gemm_grid_cap, c->debug_skip, c->xattn_ctas_per_sm, c->sattn_wide, c->xattn_wg, c->fuse_ln_gemv};
   auto it = m->step_graphs.find(key);
   if (it == m->step_graphs.end()) {
     if (m->step_graphs.size() > 64) {
@@ -723,6 +750,8 @@ void omni_decode_impl(Ctx* c, const int64_t* pt_prompt, int n_prompt, const alm_
   const bool pt_clamped = pt_steps < cfg.pt_seq_length;
   ALM_REQUIRE(cfg.vie_categories == m->vie, ALM_ERR_INVALID, "vie_categories does not match the loaded checkpoint");
   ALM_REQUIRE(kie == (m->vie > 0), ALM_ERR_INVALID, "use alm_omni_decode for text spotting and alm_omni_decode_kie for KIE");
+  ALM_REQUIRE(m->kv_decoders == 3 || points_only, ALM_ERR_STATE,
+              "the batch was encoded with kv_decoders < 3: only alm_omni_decode_points can run on it");
   ALM_REQUIRE(points_only || cfg.max_instances >= (pt_steps / 2), ALM_ERR_INVALID, "max_instances < pt_seq_length / 2");
   ALM_REQUIRE(points_only || cfg.poly_length == 32, ALM_ERR_UNSUPPORTED, "polygon length is fixed at 32 (transformer.py:254)");
   const int B = m->B;
@@ -962,6 +991,7 @@ void omni_decode_logits(Ctx* c, int image, int kind, const int64_t* seq, int n_s
   ALM_REQUIRE(c->xattn_impl != 1 || m->vt_hi, ALM_ERR_STATE, "xattn_impl 1 must be set before alm_omni_encode");
   ALM_REQUIRE(image >= 0 && image < m->B && kind >= 0 && kind < 3 && n_seq > 0 && len > 0 && len <= 1024,
               ALM_ERR_INVALID, "decode_logits arguments");
+  ALM_REQUIRE(kind < m->kv_decoders, ALM_ERR_STATE, "the batch was encoded without this decoder's K/V cache (kv_decoders)");
   Arena& ws = c->ws;
   ws.release(m->ws_mark);
   std::vector<int> h(static_cast<size_t>(n_seq) * len);

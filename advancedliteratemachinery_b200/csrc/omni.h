@@ -62,6 +62,7 @@ struct OmniModel {
 
   // ---- state of the last alm_omni_encode -------------------------------------------------------
   bool encoded = false;
+  int kv_decoders = 3;  // decoders whose K/V caches the last encode filled
   int B = 0, H = 0, W = 0;
   int Hs[4] = {0, 0, 0, 0}, Ws[4] = {0, 0, 0, 0};
   int mh = 0, mw = 0, M = 0, Mpad = 0;

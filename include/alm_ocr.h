@@ -80,9 +80,14 @@ ALM_API const char* alm_version(void);
 /* options: "nsplit" (3 = bf16x3 split operands, fp32-class results [default]; 1 = single-pass bf16),
  *          "gemm_impl" (0 = tcgen05 [default], 1 = SIMT debug kernel), "workspace_mb", "profile_gemm",
  *          "trace_gemm" (capacity; see alm_trace_read), "trace_detail" (see alm_bench_gemm_ex),
- *          "attn_impl" (ViT attention of MGP-STR: 0 = fused tcgen05 kernel, scores / probabilities in tensor memory;
- *          1 = score GEMM + softmax + P.V GEMM, the A/B reference),
- *          "wattn_impl" (0 = tensor-core window attention [default], 1 = fp32 SIMT debug kernel),
+ *          "fuse_ln_gemv" (point loop: 1 = every pre-LayerNorm runs inside the GEMV that consumes it, 13 fewer dependent
+ *          launches per token [default]; 0 = separate LayerNorm launches),
+ *          "kv_decoders" (3 = alm_omni_encode fills the cross-attention K/V caches of the pt, poly and rec decoders
+ *          [default]; 1 = only the point decoder's, for callers that run alm_omni_decode_points alone),
+ *          "attn_impl" (ViT attention of MGP-STR: 0 = fused tcgen05 kernel, scores / probabilities in tensor memory
+ *          [default]; 1 = score GEMM + softmax + P.V GEMM, the A/B reference),
+ *          "wattn_impl" (0 = mma.sync window attention [default], 1 = fp32 SIMT debug kernel, 2 = tcgen05 kernel with
+ *          TMA-staged window tiles, two windows per M = 128 tile, scores / probabilities in tensor memory),
  *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
  *          streams / in-flight batches can share the GPU),
  *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
