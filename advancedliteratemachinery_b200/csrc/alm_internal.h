@@ -202,6 +202,7 @@ struct Ctx {
   cudaEvent_t ev_order = nullptr;  // alm_stream_wait / alm_stream_release
   cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync event: host waits that sleep instead of spinning
   int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
+  int gemm_plain_epilogue = 1;  // 1 = map-free launches use the slim epilogue specialisation (A/B: 0)
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
   int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial
   int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps
@@ -213,7 +214,7 @@ struct Ctx {
   int xattn_wg = 1;  // 2 = 8-warp variant of the 64-query fused cross-attention (two key groups per block)
   int xattn_ctas_per_sm = 2;  // persistent grid of the fused cross-attention kernel
   int xattn_impl = 0;  // 0 = fused flash-style cross-attention (xattn.cu), 1 = score GEMM + softmax + P.V GEMM,
-                       // 2 = fused, TMA + mbarrier pipeline (xattn_tma.cu; experimental)
+                       // 2 = fused, TMA + mbarrier pipeline (xattn_tma.cu), 3 = tcgen05 + TMA ring (xattn_tc.cu)
   int fuse_ln_gemv = 1;  // point loop: 1 = the pre-LayerNorms run inside the following GEMV (13 fewer dependent launches per token)
   int kv_decoders = 3;  // number of decoders (pt, poly, rec order) whose cross-attention K/V caches alm_omni_encode fills
   int attn_impl = 0;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM

@@ -184,7 +184,7 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
         ALM_CHECK_CUDA(cudaMemset(h->c.detail_buf, 0, 64 * 6 * sizeof(unsigned long long)));
       }
     } else if (k == "xattn_impl") {
-      ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "xattn_impl must be 0, 1 or 2");
+      ALM_REQUIRE(value >= 0 && value <= 3, ALM_ERR_INVALID, "xattn_impl must be 0..3");
       h->c.xattn_impl = static_cast<int>(value);
     } else if (k == "fuse_ln_gemv") {
       h->c.fuse_ln_gemv = value ? 1 : 0;
@@ -215,6 +215,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
       h->c.decode_priority = value ? 1 : 0;
     } else if (k == "small_grid_cap") {
       h->c.small_grid_cap = static_cast<int>(value);
+    } else if (k == "gemm_plain_epilogue") {
+      h->c.gemm_plain_epilogue = value ? 1 : 0;
     } else if (k == "wide_tiles") {
       h->c.wide_tiles = value ? 1 : 0;
     } else if (k == "decode_streams") {

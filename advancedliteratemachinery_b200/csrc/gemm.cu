@@ -88,35 +88,78 @@ __device__ __forceinline__ void split_pack_bf16x2(float x, float y, uint32_t& hi
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
 }
 
+// The same GELU on a PAIR of values with the packed fp32x2 pipe (FFMA2 / FMUL2): the polynomial, the products and the
+// final blend are one instruction per pair; only the two MUFU ops and the sign transfer stay per lane.
+//   erf(|x|/sqrt2) = 1 - p(t) t e,  t = 1 / (1 + 0.3275911 |x|/sqrt2),  e = 2^(-x^2 log2(e) / 2)
+__device__ __forceinline__ f2 gelu_erf2(f2 x) {
+  float x0, x1;
+  f2_get(x, x0, x1);
+  const f2 ax = f2_make(fabsf(x0), fabsf(x1));
+  const f2 den = f2_fma(f2_splat(0.3275911f * 0.70710678118654752440f), ax, f2_splat(1.0f));
+  const f2 arg = f2_mul(f2_mul(x, x), f2_splat(-0.5f * 1.4426950408889634f));
+  float d0, d1, a0, a1, t0, t1, e0, e1;
+  f2_get(den, d0, d1);
+  f2_get(arg, a0, a1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f2 t = f2_make(t0, t1), e = f2_make(e0, e1);
+  // q = -p(t): the Abramowitz-Stegun 7.1.26 coefficients with flipped signs, so that erf = 1 + q t e is one fma
+  f2 q = f2_fma(t, f2_splat(-1.061405429f), f2_splat(1.453152027f));
+  q = f2_fma(t, q, f2_splat(-1.421413741f));
+  q = f2_fma(t, q, f2_splat(0.284496736f));
+  q = f2_fma(t, q, f2_splat(-0.254829592f));
+  const f2 erf_abs = f2_fma(f2_mul(q, t), e, f2_splat(1.0f));
+  float r0, r1;
+  f2_get(erf_abs, r0, r1);
+  const f2 serf = f2_make(copysignf(r0, x0), copysignf(r1, x1));
+  const f2 h = f2_mul(x, f2_splat(0.5f));
+  return f2_fma(h, serf, h);   // 0.5 x (1 + erf)
+}
+
 // Epilogue inner loop for one thread: 8 rows x 4 consecutive columns, everything already in registers.
 // Compile-time activation / output kinds keep this a short branch-free instruction stream (the epilogue warps
-// have one or two warps per scheduler, so instruction count is what bounds small-K GEMMs).
-template <int ACT, int F32, int SPLIT>
+// have one or two warps per scheduler, so instruction count is what bounds small-K GEMMs); the arithmetic runs on
+// fp32 pairs (alpha / bias fma, GELU, residual add, the hi/lo split) -- half the FMA-pipe instructions.
+template <int ACT, int F32, int SPLIT, int ROWBIAS>
 __device__ __forceinline__ void epi_store8(const float4 (&acc)[8], const int (&orow)[8], const float (&rbias)[8],
                                            const float4 (&res)[8], const float4& bb, float alpha, long ocol, long ldo,
                                            float* __restrict__ out_f32, bf16* __restrict__ out_hi,
                                            bf16* __restrict__ out_lo) {
+  const f2 al = f2_splat(alpha);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (orow[i] < 0) continue;
-    float f0 = fmaf(acc[i].x, alpha, rbias[i] + bb.x), f1 = fmaf(acc[i].y, alpha, rbias[i] + bb.y);
-    float f2 = fmaf(acc[i].z, alpha, rbias[i] + bb.z), f3 = fmaf(acc[i].w, alpha, rbias[i] + bb.w);
-    if (ACT == ACT_GELU) { f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3); }
-    if (ACT == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
-    f0 += res[i].x; f1 += res[i].y; f2 += res[i].z; f3 += res[i].w;
+    const float rb = ROWBIAS ? rbias[i] : 0.f;
+    f2 a = f2_fma(f2_make(acc[i].x, acc[i].y), al, ROWBIAS ? f2_make(rb + bb.x, rb + bb.y) : f2_make(bb.x, bb.y));
+    f2 b = f2_fma(f2_make(acc[i].z, acc[i].w), al, ROWBIAS ? f2_make(rb + bb.z, rb + bb.w) : f2_make(bb.z, bb.w));
+    if (ACT == ACT_GELU) { a = gelu_erf2(a); b = gelu_erf2(b); }
+    if (ACT == ACT_RELU) {
+      float u0, u1, u2, u3;
+      f2_get(a, u0, u1); f2_get(b, u2, u3);
+      a = f2_make(fmaxf(u0, 0.f), fmaxf(u1, 0.f)); b = f2_make(fmaxf(u2, 0.f), fmaxf(u3, 0.f));
+    }
+    a = f2_add(a, f2_make(res[i].x, res[i].y));
+    b = f2_add(b, f2_make(res[i].z, res[i].w));
+    float f0, f1, f2_, f3;
+    f2_get(a, f0, f1); f2_get(b, f2_, f3);
     const long o = ocol + static_cast<long>(orow[i]) * ldo;
-    if (F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(f0, f1, f2, f3);
+    if (F32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(f0, f1, f2_, f3);
     if (SPLIT) {
       uint32_t h01, l01, h23, l23;
       split_pack_bf16x2(f0, f1, h01, l01);
-      split_pack_bf16x2(f2, f3, h23, l23);
+      split_pack_bf16x2(f2_, f3, h23, l23);
       *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h01, h23);
       if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l01, l23);
     }
   }
 }
 
-template <int BLOCK_N, int NSPLIT>
+// PLAIN = 1: the epilogue of a map-free launch (no output / residual row maps, no per-row bias, vector-aligned
+// outputs): the row bookkeeping collapses to "row < M" and none of the predicated map / row-bias loads of the generic
+// epilogue are even issued (ncu: those option paths were ~1/3 of the executed instructions of a GELU epilogue).
+template <int BLOCK_N, int NSPLIT, int PLAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -307,12 +350,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           acc[i] = *reinterpret_cast<const float4*>(stg + rl * 32 + ((j4 ^ (rl & 7)) << 2));
           const int row = row_base + rl;
           int o = (row < p.M && col_ok) ? row : -1;
-          if (o >= 0 && e.out_map) o = e.out_map[row];
+          if (!PLAIN && o >= 0 && e.out_map) o = e.out_map[row];
           orow[i] = o;
-          rrow[i] = (o >= 0 && e.resid_map) ? e.resid_map[row] : o;
-          rbias[i] = (o >= 0 && bias && e.bias_mode == BIAS_ROW) ? bias[row] : 0.0f;
+          rrow[i] = (!PLAIN && o >= 0 && e.resid_map) ? e.resid_map[row] : o;
+          rbias[i] = (!PLAIN && o >= 0 && bias && e.bias_mode == BIAS_ROW) ? bias[row] : 0.0f;
         }
-        if (vec) {
+        if (PLAIN || vec) {
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias && e.bias_mode == BIAS_COL) bb = *reinterpret_cast<const float4*>(bias + col);
           float4 res[8];
@@ -327,7 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           switch (kind) {
 #define ALM_EPI_CASE(ACTV, F32V, SPLV)                                                                         \
   case (ACTV) * 4 + (F32V) + 2 * (SPLV):                                                                        \
-    epi_store8<ACTV, F32V, SPLV>(acc, orow, rbias, res, bb, e.alpha, ocol, e.ldo, e.out_f32, e.out_hi, e.out_lo); \
+    epi_store8<ACTV, F32V, SPLV, !PLAIN>(acc, orow, rbias, res, bb, e.alpha, ocol, e.ldo, e.out_f32, e.out_hi, e.out_lo); \
     break;
             ALM_EPI_CASE(0, 1, 0) ALM_EPI_CASE(0, 0, 1) ALM_EPI_CASE(0, 1, 1)
             ALM_EPI_CASE(1, 1, 0) ALM_EPI_CASE(1, 0, 1) ALM_EPI_CASE(1, 1, 1)
@@ -335,7 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #undef ALM_EPI_CASE
             default: break;
           }
-        } else {
+        } else if (!PLAIN) {
           // ragged / unaligned tail: scalar, guarded (fully unrolled so the row arrays stay in registers)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -486,11 +529,11 @@ const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int bo
   return c->tmap_cache.emplace(key, tm).first->second;
 }
 
-template <int BLOCK_N, int NSPLIT>
+template <int BLOCK_N, int NSPLIT, int PLAIN>
 void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   using L = SmemLayout<BLOCK_N, NSPLIT>;
   static DeviceOnce attr_set;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, NSPLIT>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, NSPLIT, PLAIN>;
   if (attr_set.need()) {
     ALM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     pin_carveout(kern);
@@ -576,15 +619,23 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
     // 256 output columns (96 KB per K-step for twice the MMA work of a 128-wide tile's 64 KB).
     const bool wide = !narrow && c->wide_tiles && p.N >= 256 && (p.N % 256 == 0 || p.N >= 1024) &&
                       static_cast<long>(p.m_blocks) * ((p.N + 255) / 256) * p.nb0 * p.nb1 >= 2L * c->num_sms;
+    // map-free, vector-aligned launches take the slim epilogue
+    const bool plain = c->gemm_plain_epilogue && !E.out_map && !E.resid_map && E.bias_mode != BIAS_ROW && vec && p.N % 4 == 0;
+#define ALM_LAUNCH(BNV, NSV)                                  \
+  do {                                                        \
+    if (plain) launch_tc<BNV, NSV, 1>(c, A, B, p);            \
+    else launch_tc<BNV, NSV, 0>(c, A, B, p);                  \
+  } while (0)
     if (nsplit == 3) {
-      if (narrow) launch_tc<32, 3>(c, A, B, p);
-      else if (wide) launch_tc<256, 3>(c, A, B, p);
-      else launch_tc<128, 3>(c, A, B, p);
+      if (narrow) ALM_LAUNCH(32, 3);
+      else if (wide) ALM_LAUNCH(256, 3);
+      else ALM_LAUNCH(128, 3);
     } else {
-      if (narrow) launch_tc<32, 1>(c, A, B, p);
-      else if (wide) launch_tc<256, 1>(c, A, B, p);
-      else launch_tc<128, 1>(c, A, B, p);
+      if (narrow) ALM_LAUNCH(32, 1);
+      else if (wide) ALM_LAUNCH(256, 1);
+      else ALM_LAUNCH(128, 1);
     }
+#undef ALM_LAUNCH
   }
   if (c->profile_gemm) {
     ALM_CHECK_CUDA(cudaEventRecord(rec.b, c->stream));

@@ -435,7 +435,8 @@ struct DecodeBufs {
   int xq_splits = 1;
   int mq_grid = 1, mq_parts = 1;  // fused cross-attention: persistent grid size, partial slots per (image, head, query block)
   bool fused_xattn = false;
-  bool tma_xattn = false;  // fused, experimental TMA + mbarrier variant (xattn_impl 2)
+  bool tma_xattn = false;  // fused, TMA + mbarrier variant of the mma.sync kernel (xattn_impl 2)
+  bool tc_xattn = false;   // fused, tcgen05 + TMA ring (xattn_impl 3)
   SplitBuf prob;
   float* kc[4] = {nullptr, nullptr, nullptr, nullptr};
   float* vc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -466,11 +467,13 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     d.h1f = c->ws.get<float>(S * 512);
     d.qkv = c->ws.get<float>(S * 1536);
   }
-  if (c->xattn_impl == 0 || c->xattn_impl == 2) {
+  if (c->xattn_impl == 0 || c->xattn_impl == 2 || c->xattn_impl == 3) {
     int pairs = 0;
     d.fused_xattn = true;
     d.tma_xattn = c->xattn_impl == 2;
-    if (d.tma_xattn) cross_attn_tma_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
+    d.tc_xattn = c->xattn_impl == 3;
+    if (d.tc_xattn) cross_attn_tc_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
+    else if (d.tma_xattn) cross_attn_tma_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
     else cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
     d.xq_partial = c->ws.get<float>(cross_attn_mq_partial_floats(pairs, d.mq_parts));
     d.xq_counters = c->ws.get<int>(pairs);
@@ -497,6 +500,12 @@ void fused_xattn(Ctx* c, OmniModel* m, DecodeBufs& u, const bf16* q_hi, const bf
                  int Ncap, long dl, bf16* out_hi, bf16* out_lo, float* out_f32) {
   const int M = m->M;
   const uint8_t* kpm = m->kpm + static_cast<long>(img0) * M;
+  if (u.tc_xattn) {
+    cross_attn_tc(c, q_hi, q_lo, q_f32, nimg, Ncap, m->kc_hi, m->kc_lo, m->vc_hi, m->vc_lo, static_cast<long>(m->B) * 96,
+                  static_cast<int>(img0 * 96 + dl * 8), kpm, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters, out_hi, out_lo,
+                  out_f32);
+    return;
+  }
   if (u.tma_xattn) {
     cross_attn_tma(c, q_hi, q_lo, q_f32, nimg, Ncap, m->kc_hi, m->kc_lo, m->vc_hi, m->vc_lo, static_cast<long>(m->B) * 96,
                    static_cast<int>(img0 * 96 + dl * 8), kpm, M, u.mq_grid, u.mq_parts, u.xq_partial, u.xq_counters, out_hi,

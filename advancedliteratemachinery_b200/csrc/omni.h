@@ -126,6 +126,11 @@ void cross_attn_tma_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_
 void cross_attn_tma(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
                     const bf16* kc_lo, const bf16* vc_hi, const bf16* vc_lo, long slices, int z0, const uint8_t* kpm, int M,
                     int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo, float* out_f32);
+// tcgen05 + TMA-ring variant (xattn_tc.cu, "xattn_impl" 3): 128-key blocks, S / P in tensor memory, one CTA per SM
+void cross_attn_tc_plan(Ctx* c, int nimg, int Ncap, int M, int* grid, int* max_parts, int* pairs);
+void cross_attn_tc(Ctx* c, const bf16* q_hi, const bf16* q_lo, const float* q_f32, int nimg, int Ncap, const bf16* kc_hi,
+                   const bf16* kc_lo, const bf16* vc_hi, const bf16* vc_lo, long slices, int z0, const uint8_t* kpm, int M,
+                   int grid, int max_parts, float* partial, int* counters, bf16* out_hi, bf16* out_lo, float* out_f32);
 void add_i32(Ctx* c, int* p, int v);
 void build_inst_prompts(Ctx* c, const int* pt_tokens, int pt_stride, int n_prompt, const int* ntok, int B, int Ncap,
                         int sos, int* tokens, int tstride);

@@ -38,7 +38,8 @@ struct WtSmem {
   static constexpr int kStage = 3 * NP * WT_TILE;       // q, k, v of every plane
   static constexpr int kBar = WT_STAGES * kStage;
   static constexpr int kReg = kBar + 128;               // region ids of the 98 tokens of the tile being soft-maxed
-  static constexpr int kTotal = kReg + 128 * 4 + 1024;  // + alignment slack
+  static constexpr int kBias = kReg + 128 * 4;          // dense relative-position bias of the current head pair [2][49*49]
+  static constexpr int kTotal = kBias + 2 * 2404 * 4 + 1024;  // + alignment slack
 };
 
 struct WtParams {
@@ -73,6 +74,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   uint64_t* o_empty = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   int* sreg = reinterpret_cast<int*>(smem + L::kReg);
+  float* sbias = reinterpret_cast<float*>(smem + L::kBias);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t S_COL[2] = {0, 128}, P_COL[2] = {256, 320}, O_COL[2] = {384, 448};
@@ -189,6 +191,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     // 16-column chunks this warp must look at: windows 0 / 1 own key columns [0,49) / [49,98)
     const int c_lo = quarter <= 1 ? 0 : 3, c_hi = quarter == 0 ? 4 : 7;
     uint32_t s_phase = 0, o_phase = 0;
+    int cur_hp = -1;
     const int wins_per_img = p.nWh * p.nWw;
     for (long it = it_begin; it < it_end; ++it) {
       const int hp = static_cast<int>(it / p.n_pairs);
@@ -202,8 +205,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         const int rw = ww < p.Wp - 7 ? 0 : (ww < p.Wp - p.shift ? 1 : 2);
         reg = rh * 3 + rw;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous item's readers of sreg are done
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous item's readers of sreg / sbias are done
       sreg[r] = reg;
+      if (hp != cur_hp) {   // the CTA's run is head-pair-major: the two 49 x 49 bias tables change rarely.  Read per
+        cur_hp = hp;        // token ROW from shared memory the stride (49 words) is odd, i.e. bank-conflict free; the same
+                            // reads straight from global memory cost 32 L1 wavefronts per instruction.
+        const float* src = p.bias + static_cast<long>(2 * hp) * 2401;
+        for (int i = threadIdx.x - 64; i < 2 * 2401; i += 128) sbias[(i / 2401) * 2404 + i % 2401] = __ldg(src + i);
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       ptx::mbar_wait(s_full, s_phase);
       s_phase ^= 1;
@@ -212,7 +221,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       const int key0 = 49 * w;
 #pragma unroll
       for (int hd = 0; hd < 2; ++hd) {
-        const float* bias_row = p.bias + (static_cast<long>(2 * hp + hd) * 49 + (live ? ti : 0)) * 49 - key0;
+        const float* bias_row = sbias + hd * 2404 + (live ? ti : 0) * 49 - key0;
         // pass 1: row maximum of s + bias + mask over the 49 keys of the row's window
         float m = -INFINITY;
         for (int c = c_lo; c < c_hi; ++c) {
@@ -223,7 +232,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
           for (int j = 0; j < 16; ++j) {
             const int col = c * 16 + j;
             if (live && col >= key0 && col < key0 + 49) {
-              float x = __uint_as_float(v[j]) + __ldg(bias_row + col);
+              float x = __uint_as_float(v[j]) + bias_row[col];
               if (p.shift > 0 && sreg[col] != reg) x += -100.0f;
               m = fmaxf(m, x);
             }
@@ -245,7 +254,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
                 const int col = c * 16 + j + q;
                 e[q] = 0.f;
                 if (live && col >= key0 && col < key0 + 49) {
-                  float x = __uint_as_float(v[j + q]) + __ldg(bias_row + col);
+                  float x = __uint_as_float(v[j + q]) + bias_row[col];
                   if (p.shift > 0 && sreg[col] != reg) x += -100.0f;
                   e[q] = __expf(x - m);
                 }

@@ -90,12 +90,14 @@ ALM_API const char* alm_version(void);
  *          TMA-staged window tiles, two windows per M = 128 tile, scores / probabilities in tensor memory),
  *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
  *          streams / in-flight batches can share the GPU),
+ *          "gemm_plain_epilogue" (1 = map-free GEMM launches use the slim epilogue specialisation [default], 0 = generic),
  *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
  *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager),
  *          "xattn_impl" (0 = fused flash-style decoder cross-attention [default]; 1 = unfused score GEMM + softmax +
- *          P.V GEMM / fp32 single-query kernel, the A/B reference -- must be set before alm_omni_encode; 2 = fused with a
- *          TMA + mbarrier operand pipeline, experimental),
+ *          P.V GEMM / fp32 single-query kernel, the A/B reference -- must be set before alm_omni_encode; 2 = the mma.sync
+ *          kernel with a TMA + mbarrier operand ring; 3 = tcgen05 kernel: 128-key TMA ring, scores / probabilities in
+ *          tensor memory, running output in registers),
  *          "xattn_ctas_per_sm" (persistent grid of the fused cross-attention: 1..3 CTAs per SM, default 2),
  *          "sattn_wide" (1 = CTA per (sequence, head) self-attention step when few sequences are live [default]),
  *          "enc_grid_cap" / "dec_grid_cap" (0 = off [default]; n = GEMM launches of alm_omni_encode / of the decode

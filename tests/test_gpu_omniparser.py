@@ -414,9 +414,11 @@ def test_more_than_32_pages_leave_the_skinny_path_and_stay_batch_invariant():
                     assert torch.equal(x, y)
 
 
-def test_tma_cross_attention_variant_matches_the_default_kernel():
-    """`xattn_impl` 2 (csrc/xattn_tma.cu) against the default fused kernel: 70 / 33 sequences (8 math warps), 10 and 1
-    (the 16-row pt variant), ragged key range, masked keys, two images, then a whole greedy decode."""
+@pytest.mark.parametrize('impl', [2, 3])
+def test_tma_cross_attention_variant_matches_the_default_kernel(impl):
+    """`xattn_impl` 2 (csrc/xattn_tma.cu: mma.sync with a TMA ring) and 3 (csrc/xattn_tc.cu: tcgen05, S / P in tensor
+    memory, 128-key TMA ring) against the default fused kernel: 70 / 33 sequences, 10 and 1 (the pt case), ragged key range
+    (M = 255: partial last key block), masked keys, two images, then a whole greedy decode."""
     from advancedliteratemachinery_b200 import NestedTensor
     m = model_for(0, 0.45)
     v = m.vocab
@@ -433,14 +435,14 @@ def test_tma_cross_attention_variant_matches_the_default_kernel():
             for n in (70, 33, 10, 1):
                 m.ctx.set_option('xattn_impl', 0)
                 ref = m.decode_logits(image, 'rec', seq[:n])
-                m.ctx.set_option('xattn_impl', 2)
+                m.ctx.set_option('xattn_impl', impl)
                 alt = m.decode_logits(image, 'rec', seq[:n])
                 assert torch.isfinite(alt).all()
                 assert _maxrel(alt, ref) < 2e-5, (image, n, _maxrel(alt, ref))
         m.vocab.pt_seq_length = 6
         m.ctx.set_option('xattn_impl', 0)
         a = m.forward_batch(NestedTensor(img.cuda(), mask.cuda()))
-        m.ctx.set_option('xattn_impl', 2)
+        m.ctx.set_option('xattn_impl', impl)
         b = m.forward_batch(NestedTensor(img.cuda(), mask.cuda()))
         for x, y in zip(a, b):
             assert (x is None) == (y is None)
