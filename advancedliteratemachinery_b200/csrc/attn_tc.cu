@@ -234,11 +234,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
               float e0 = c0 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc)) : 0.f;
               float e1 = c0 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc)) : 0.f;
               l += e0 + e1;
-              bf16 h0, l0, h1, l1;
-              split_bf16(e0, h0, l0);
-              split_bf16(e1, h1, l1);
-              ph[j >> 1] = pack_bf16(h0, h1);
-              pl[j >> 1] = pack_bf16(l0, l1);
+              split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
             }
             ptx::tmem_st_32x8(lane_addr + P_COL + (c0 >> 1), ph);
             if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + PLO_COL + (c0 >> 1), pl);  // behind this thread's read pointer
@@ -265,11 +261,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
                 const float x0 = __uint_as_float(v[j]) * inv, x1 = __uint_as_float(v[j + 1]) * inv;
-                bf16 h0, l0, h1, l1;
-                split_bf16(x0, h0, l0);
-                split_bf16(x1, h1, l1);
-                hh[j >> 1] = pack_bf16(h0, h1);
-                ll[j >> 1] = pack_bf16(l0, l1);
+                split_pack2_bf16(x0, x1, hh[j >> 1], ll[j >> 1]);
                 if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + orow + c0 + j) = make_float2(x0, x1);
               }
               if (p.out_hi) {

@@ -471,7 +471,10 @@ DecodeBufs alloc_decode(Ctx* c, OmniModel* m, int B, int Ncap, int Tmax) {
     int pairs = 0;
     d.fused_xattn = true;
     d.tma_xattn = c->xattn_impl == 2;
-    d.tc_xattn = c->xattn_impl == 3;
+    // the tcgen05 kernel maps one query row to one thread: right for the 64-query polygon / recognition loops, wrong for
+    // the point loop's single query per image (its 128 keys per block would be one lane's serial work) -- that keeps the
+    // mma.sync 16-row kernel, which spreads the keys of a block over the warps
+    d.tc_xattn = c->xattn_impl == 3 && Ncap > 16;
     if (d.tc_xattn) cross_attn_tc_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
     else if (d.tma_xattn) cross_attn_tma_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);
     else cross_attn_mq_plan(c, B, Ncap, m->M, &d.mq_grid, &d.mq_parts, &pairs);

@@ -249,6 +249,14 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// (x, y) -> packed bf16x2 hi and lo words with one cvt.rn.bf16x2.f32 each (hi + lo == x to ~2^-17).  F2FP runs on the
+// FMA-class pipes; the scalar __float2bfloat16_rn (F2F.BF16.F32) is an XU instruction and competes with MUFU.
+__device__ __forceinline__ void split_pack2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));  // upper half <- first source
+  const float rx = x - __uint_as_float(hi << 16);
+  const float ry = y - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }

@@ -260,11 +260,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
                 }
               }
               l += e[0] + e[1];
-              bf16 h0, l0, h1, l1;
-              split_bf16(e[0], h0, l0);
-              split_bf16(e[1], h1, l1);
-              ph[j >> 1] = pack_bf16(h0, h1);
-              pl[j >> 1] = pack_bf16(l0, l1);
+              split_pack2_bf16(e[0], e[1], ph[j >> 1], pl[j >> 1]);
             }
           } else {
 #pragma unroll
@@ -298,11 +294,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const float x0 = __uint_as_float(v[j]) * inv_l[hd], x1 = __uint_as_float(v[j + 1]) * inv_l[hd];
-              bf16 h0, l0, h1, l1;
-              split_bf16(x0, h0, l0);
-              split_bf16(x1, h1, l1);
-              hh[j >> 1] = pack_bf16(h0, h1);
-              ll[j >> 1] = pack_bf16(l0, l1);
+              split_pack2_bf16(x0, x1, hh[j >> 1], ll[j >> 1]);
               if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + obase + hd * 32 + c0 + j) = make_float2(x0, x1);
             }
             const long o = obase + hd * 32 + c0;

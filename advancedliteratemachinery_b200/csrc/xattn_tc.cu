@@ -300,51 +300,40 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
         ptx::tc_fence_after();
         float m_blk = -INFINITY, l_blk = 0.f;
         if (warp_live) {
+          // key-padding mask of the block as 4 x 32 bits, fetched once (one memory round trip, no alignment assumption):
+          // lane L looks at keys L, L + 32, L + 64, L + 96 of the block; a ballot hands every lane all 128 bits
+          uint32_t mw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int key = key0 + 32 * j + lane;
+            const bool masked = key >= p.M || (kpm != nullptr && kpm[key < p.M ? key : 0] != 0);
+            mw[j] = __ballot_sync(0xffffffffu, masked);
+          }
           // pass 1: block maximum over the unmasked keys
+#pragma unroll
           for (int c0 = 0; c0 < XT_KB; c0 += 16) {
             uint32_t v[16];
             ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + c0, v);
             ptx::tmem_ld_wait();
-            const bool whole = key0 + c0 + 15 < p.M;
-            uint4 mk = make_uint4(0, 0, 0, 0);
-            if (kpm && whole) mk = *reinterpret_cast<const uint4*>(kpm + key0 + c0);
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t bits = mw[c0 >> 5] >> (c0 & 31);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int key = key0 + c0 + j;
-              bool masked;
-              if (whole) masked = ((mw[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0;
-              else masked = key >= p.M || (kpm && kpm[key] != 0);
-              if (!masked) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-            }
+            for (int j = 0; j < 16; ++j)
+              if (!((bits >> j) & 1u)) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
           }
           // pass 2: p = 2^((s - m_b) c), block sum, bf16 (hi, lo) pairs back into tensor memory
           const float mc = m_blk == -INFINITY ? 0.f : m_blk * p.scale_log2e;
+#pragma unroll
           for (int c0 = 0; c0 < XT_KB; c0 += 16) {
             uint32_t v[16], ph[8], pl[8];
             ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + c0, v);
             ptx::tmem_ld_wait();
-            const bool whole = key0 + c0 + 15 < p.M;
-            uint4 mk = make_uint4(0, 0, 0, 0);
-            if (kpm && whole) mk = *reinterpret_cast<const uint4*>(kpm + key0 + c0);
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t bits = (mw[c0 >> 5] >> (c0 & 31)) | (live ? 0u : 0xffffu);
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float e[2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int key = key0 + c0 + j + q;
-                bool masked;
-                if (whole) masked = ((mw[(j + q) >> 2] >> (8 * ((j + q) & 3))) & 0xffu) != 0;
-                else masked = key >= p.M || (kpm && kpm[key] != 0);
-                e[q] = (masked || !live) ? 0.f : xt_ex2(fmaf(__uint_as_float(v[j + q]), p.scale_log2e, -mc));
-              }
-              l_blk += e[0] + e[1];
-              bf16 h0, l0, h1, l1;
-              split_bf16(e[0], h0, l0);
-              split_bf16(e[1], h1, l1);
-              ph[j >> 1] = pack_bf16(h0, h1);
-              pl[j >> 1] = pack_bf16(l0, l1);
+              const float e0 = ((bits >> j) & 1u) ? 0.f : xt_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc));
+              const float e1 = ((bits >> (j + 1)) & 1u) ? 0.f : xt_ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc));
+              l_blk += e0 + e1;
+              split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
             }
             ptx::tmem_st_32x8(lane_addr + P_COL[buf] + (c0 >> 1), ph);
             if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + S_COL[buf] + (c0 >> 1), pl);   // behind this thread's read pointer
@@ -377,13 +366,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
           if (p.out_hi) {
             uint32_t hh[4], ll[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              bf16 h0, l0, h1, l1;
-              split_bf16(x[2 * j], h0, l0);
-              split_bf16(x[2 * j + 1], h1, l1);
-              hh[j] = pack_bf16(h0, h1);
-              ll[j] = pack_bf16(l0, l1);
-            }
+            for (int j = 0; j < 4; ++j) split_pack2_bf16(x[2 * j], x[2 * j + 1], hh[j], ll[j]);
             *reinterpret_cast<uint4*>(p.out_hi + orow + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + orow + c0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
           }
