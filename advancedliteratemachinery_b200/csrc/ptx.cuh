@@ -24,6 +24,19 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// explicit shared-state-space loads (a pointer derived from an aligned-up `extern __shared__` base is generic to nvcc,
+// which would emit LD instead of LDS)
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t saddr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

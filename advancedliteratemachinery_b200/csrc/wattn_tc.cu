@@ -13,7 +13,8 @@
 // the qkv weight at load time).
 //
 // One persistent CTA per SM; item = (window pair, head pair).  Warp 0 = TMA producer over a 2-stage ring (q, k, v tiles of
-// hi and lo planes: 6 x 98 rows x 128 B per item, no over-read), warp 1 = MMA issuer, warps 2..5 = softmax + epilogue.
+// hi and lo planes: 6 x 98 rows x 128 B per item, no over-read), warp 1 = MMA issuer, warps 2..5 / 6..9 = softmax + epilogue of
+// head 0 / head 1 of the pair (thread = token row).
 // TMEM (512 columns): S of head 0 / head 1 at 0 / 128 (112 used each; the low halves of P overwrite them in place),
 // P_hi at 256 / 320, O at 384 / 448 (each P.V runs 64 wide over both heads' channels; the epilogue keeps its own half).
 #include <algorithm>
@@ -25,7 +26,7 @@ namespace alm {
 
 namespace {
 
-constexpr int WT_THREADS = 192;
+constexpr int WT_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2..5 softmax of head 0, warps 6..9 of head 1
 constexpr int WT_ROWS = 98;                 // two windows
 constexpr int WT_NK = 112;                  // keys padded to the UMMA N granularity
 constexpr int WT_TILE = 128 * 128;          // bytes of one operand tile in shared memory (128 rows x 64 bf16)
@@ -94,9 +95,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       ptx::mbar_init(&in_empty[s], 1);
     }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(p_full, 8);
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_empty, 4);
+    ptx::mbar_init(o_empty, 8);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -182,17 +183,22 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     }
   } else {
     // ================================================================================= softmax + epilogue warps
-    const int quarter = warp & 3;
+    // two warp groups, one per head of the pair: both heads' softmaxes run concurrently, two warps per scheduler
+    const int quarter = warp & 3, hd = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
+    const uint32_t s_col = hd * 128, p_col = 256 + hd * 64, o_col = 384 + hd * 64;   // == S_COL / P_COL / O_COL [hd]
     const int r = quarter * 32 + lane;          // token row of the tile
     const int w = r >= 49 ? 1 : 0;              // which of the two windows
     const int ti = r - 49 * w;                  // token index inside the window (>= 49: idle row)
     const bool live = r < WT_ROWS;
     // 16-column chunks this warp must look at: windows 0 / 1 own key columns [0,49) / [49,98)
     const int c_lo = quarter <= 1 ? 0 : 3, c_hi = quarter == 0 ? 4 : 7;
+    const int key0 = 49 * w;
     uint32_t s_phase = 0, o_phase = 0;
     int cur_hp = -1;
     const int wins_per_img = p.nWh * p.nWw;
+    const uint32_t sreg_s = ptx::smem_u32(sreg), sbias_s = ptx::smem_u32(sbias);
+    constexpr float kLog2e = 1.4426950408889634f;
     for (long it = it_begin; it < it_end; ++it) {
       const int hp = static_cast<int>(it / p.n_pairs);
       const long wp = it % p.n_pairs;
@@ -205,109 +211,104 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         const int rw = ww < p.Wp - 7 ? 0 : (ww < p.Wp - p.shift ? 1 : 2);
         reg = rh * 3 + rw;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous item's readers of sreg / sbias are done
-      sreg[r] = reg;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous item's readers of sreg / sbias are done
+      if (hd == 0) sreg[r] = reg;
       if (hp != cur_hp) {   // the CTA's run is head-pair-major: the two 49 x 49 bias tables change rarely.  Read per
-        cur_hp = hp;        // token ROW from shared memory the stride (49 words) is odd, i.e. bank-conflict free; the same
-                            // reads straight from global memory cost 32 L1 wavefronts per instruction.
+        cur_hp = hp;        // token ROW from shared memory the stride (49 words) is odd, i.e. bank-conflict free (the same
+                            // reads straight from global memory cost 32 L1 wavefronts per instruction).  Stored x log2(e):
+                            // the softmax below works in base 2.
         const float* src = p.bias + static_cast<long>(2 * hp) * 2401;
-        for (int i = threadIdx.x - 64; i < 2 * 2401; i += 128) sbias[(i / 2401) * 2404 + i % 2401] = __ldg(src + i);
+        for (int i = threadIdx.x - 64; i < 2 * 2401; i += 256) sbias[(i / 2401) * 2404 + i % 2401] = __ldg(src + i) * kLog2e;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(s_full, s_phase);
       s_phase ^= 1;
       ptx::tc_fence_after();
-      float inv_l[2] = {1.f, 1.f};
-      const int key0 = 49 * w;
+      const uint32_t bias_row = sbias_s + 4u * static_cast<uint32_t>(hd * 2404 + (live ? ti : 0) * 49 - key0);
+      const bool shifted = p.shift > 0;
+      // pass 1: row maximum of x = (s + bias + mask) log2(e) over the 49 keys of the row's window
+      float m = -INFINITY;
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(lane_addr + s_col + c * 16, v);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int hd = 0; hd < 2; ++hd) {
-        const float* bias_row = sbias + hd * 2404 + (live ? ti : 0) * 49 - key0;
-        // pass 1: row maximum of s + bias + mask over the 49 keys of the row's window
-        float m = -INFINITY;
-        for (int c = c_lo; c < c_hi; ++c) {
+        for (int j = 0; j < 16; ++j) {
+          const int col = c * 16 + j;
+          if (live && col >= key0 && col < key0 + 49) {
+            float x = fmaf(__uint_as_float(v[j]), kLog2e, ptx::lds_f32(bias_row + 4u * col));
+            if (shifted && ptx::lds_s32(sreg_s + 4u * col) != reg) x += -100.0f * kLog2e;
+            m = fmaxf(m, x);
+          }
+        }
+      }
+      // pass 2: p = 2^(x - m), row sum, bf16 (hi, lo) pairs back into tensor memory; keys outside the window get 0
+      float l = 0.f;
+      for (int c = 0; c < WT_NK / 16; ++c) {
+        uint32_t ph[8], pl[8];
+        if (c >= c_lo && c < c_hi) {
           uint32_t v[16];
-          ptx::tmem_ld_32x16(lane_addr + S_COL[hd] + c * 16, v);
+          ptx::tmem_ld_32x16(lane_addr + s_col + c * 16, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c * 16 + j;
-            if (live && col >= key0 && col < key0 + 49) {
-              float x = __uint_as_float(v[j]) + bias_row[col];
-              if (p.shift > 0 && sreg[col] != reg) x += -100.0f;
-              m = fmaxf(m, x);
-            }
-          }
-        }
-        // pass 2: p = exp(x - m), row sum, bf16 (hi, lo) pairs back into tensor memory; keys outside the window get 0
-        float l = 0.f;
-        for (int c = 0; c < WT_NK / 16; ++c) {
-          uint32_t ph[8], pl[8];
-          if (c >= c_lo && c < c_hi) {
-            uint32_t v[16];
-            ptx::tmem_ld_32x16(lane_addr + S_COL[hd] + c * 16, v);
-            ptx::tmem_ld_wait();
+          for (int j = 0; j < 16; j += 2) {
+            float e[2];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float e[2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int col = c * 16 + j + q;
-                e[q] = 0.f;
-                if (live && col >= key0 && col < key0 + 49) {
-                  float x = __uint_as_float(v[j + q]) + bias_row[col];
-                  if (p.shift > 0 && sreg[col] != reg) x += -100.0f;
-                  e[q] = __expf(x - m);
-                }
+            for (int q = 0; q < 2; ++q) {
+              const int col = c * 16 + j + q;
+              e[q] = 0.f;
+              if (live && col >= key0 && col < key0 + 49) {
+                float x = fmaf(__uint_as_float(v[j + q]), kLog2e, ptx::lds_f32(bias_row + 4u * col));
+                if (shifted && ptx::lds_s32(sreg_s + 4u * col) != reg) x += -100.0f * kLog2e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[q]) : "f"(x - m));
               }
-              l += e[0] + e[1];
-              split_pack2_bf16(e[0], e[1], ph[j >> 1], pl[j >> 1]);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ph[j] = pl[j] = 0u;
+            l += e[0] + e[1];
+            split_pack2_bf16(e[0], e[1], ph[j >> 1], pl[j >> 1]);
           }
-          ptx::tmem_st_32x8(lane_addr + P_COL[hd] + c * 8, ph);
-          if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + S_COL[hd] + c * 8, pl);  // behind this thread's read pointer
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ph[j] = pl[j] = 0u;
         }
-        inv_l[hd] = live ? 1.0f / l : 0.f;
+        ptx::tmem_st_32x8(lane_addr + p_col + c * 8, ph);
+        if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + s_col + c * 8, pl);  // behind this thread's read pointer
       }
+      const float inv_l = live ? 1.0f / l : 0.f;
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
-      // ---- epilogue: O / l, the two heads' 32 channels each -> 64 channels of the output planes
+      // ---- epilogue: O / l, this head's 32 channels of the output planes
       ptx::mbar_wait(o_full, o_phase);
       o_phase ^= 1;
       ptx::tc_fence_after();
       const long grow = wp * WT_ROWS + r;
       const bool store = live && grow < p.rows;
-      const long obase = grow * p.C + hp * 64;
+      const long obase = grow * p.C + hp * 64 + hd * 32;
 #pragma unroll
-      for (int hd = 0; hd < 2; ++hd)
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(lane_addr + o_col + hd * 32 + c0, v);   // head hd's own channels of the 64-wide product
+        ptx::tmem_ld_wait();
+        if (store) {
+          uint32_t hh[8], ll[8];
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t v[16];
-          ptx::tmem_ld_32x16(lane_addr + O_COL[hd] + hd * 32 + c0, v);   // head hd's own channels of the 64-wide product
-          ptx::tmem_ld_wait();
-          if (store) {
-            uint32_t hh[8], ll[8];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float x0 = __uint_as_float(v[j]) * inv_l[hd], x1 = __uint_as_float(v[j + 1]) * inv_l[hd];
-              split_pack2_bf16(x0, x1, hh[j >> 1], ll[j >> 1]);
-              if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + obase + hd * 32 + c0 + j) = make_float2(x0, x1);
-            }
-            const long o = obase + hd * 32 + c0;
-            if (p.out_hi) {
-              *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<uint4*>(p.out_hi + o + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-            }
-            if (p.out_lo) {
-              *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-              *reinterpret_cast<uint4*>(p.out_lo + o + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
-            }
+          for (int j = 0; j < 16; j += 2) {
+            const float x0 = __uint_as_float(v[j]) * inv_l, x1 = __uint_as_float(v[j + 1]) * inv_l;
+            split_pack2_bf16(x0, x1, hh[j >> 1], ll[j >> 1]);
+            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + obase + c0 + j) = make_float2(x0, x1);
+          }
+          const long o = obase + c0;
+          if (p.out_hi) {
+            *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(p.out_hi + o + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+          }
+          if (p.out_lo) {
+            *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + o + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
           }
         }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(o_empty);
