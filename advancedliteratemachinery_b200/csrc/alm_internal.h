@@ -164,6 +164,7 @@ struct Ctx {
   size_t ws_bytes = size_t(24) << 30;
   int gemm_impl = 0;  // 0 = tcgen05, 1 = SIMT debug kernel
   int nsplit = 3;     // 3 = bf16x3 split (fp32-class), 1 = single-pass bf16
+  bool lo_unused = false;  // set inside mgp_forward in single-pass mode: no kernel of that path reads lo planes
   PFN_encodeTiled encode = nullptr;
   long launches = 0;  // kernels launched since last reset (gpu_launches in bench.py)
   // memoised TMA descriptors (see gemm.cu)

@@ -322,7 +322,7 @@ void attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, long ld, int B
   p.tiles = (T + 127) / 128;
   p.items = static_cast<long>(B) * H;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
-  p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32; p.ldo = ldo;
+  p.out_hi = out_hi; p.out_lo = three ? out_lo : nullptr; p.out_f32 = out_f32; p.ldo = ldo;
   const long rows = static_cast<long>(B) * T;
   const CUtensorMap th = qkv_map(c, qkv_hi, rows, ld);
   const CUtensorMap tl = three ? qkv_map(c, qkv_lo, rows, ld) : th;

@@ -159,18 +159,8 @@ __device__ __forceinline__ void epi_store8(const float4 (&acc)[8], const int (&o
 // PLAIN = 1: the epilogue of a map-free launch (no output / residual row maps, no per-row bias, vector-aligned
 // outputs): the row bookkeeping collapses to "row < M" and none of the predicated map / row-bias loads of the generic
 // epilogue are even issued (ncu: those option paths were ~1/3 of the executed instructions of a GELU epilogue).
-// PLAIN launches run SIXTEEN epilogue warps (four per scheduler instead of two: the epilogue is a chain of dependent
-// MUFU / FMA latencies, ncu: 0.41 IPC per scheduler with two warps) on 32 x 16 accumulator chunks, which keeps them under
-// the 107-register budget of a 608-thread CTA and the staging area at the same 32 KB.
-template <int PLAIN>
-struct Roles {
-  static constexpr int kEpi = PLAIN ? 16 : 8;         // epilogue warps 2 .. 2 + kEpi - 1
-  static constexpr int kWarpB = 2 + kEpi;             // B-operand TMA producer
-  static constexpr int kThreadsT = 32 * (3 + kEpi);   // 352 / 608
-};
-
 template <int BLOCK_N, int NSPLIT, int PLAIN>
-__global__ void __launch_bounds__(Roles<PLAIN>::kThreadsT, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                     const GemmParams p) {
@@ -206,7 +196,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], Roles<PLAIN>::kEpi);  // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty[s], kEpiWarps);  // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -218,7 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   const long tiles_per_batch = static_cast<long>(p.m_blocks) * p.n_blocks;
 
-  if (warp == 0 || warp == Roles<PLAIN>::kWarpB) {
+  if (warp == 0 || warp == 10) {
     // ===================================================================== TMA producers
     // Two single-thread producers in different warps (A tiles / B tiles): a lone thread issues one bulk-tensor
     // copy every ~0.25 us, which bounds both the small-tile decode GEMMs and the big ones; two issue in parallel.
@@ -306,87 +296,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         if (p.detail && blockIdx.x == 0 && tl < 64 && lane == 0) p.detail[tl * 6 + 3] = ptx::globaltimer_ns();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-    }
-  } else if (PLAIN) {
-    // ===================================================================== epilogue warps (16), map-free launches
-    // warp -> (TMEM lane quarter, column slice): 32 x 16 accumulator chunks c = slice, slice + 4, ...  Each chunk is read
-    // row-per-thread from TMEM, transposed through a 2 KB XOR-swizzled staging block, then handled 4 columns x 4 rows per
-    // thread so that a warp's global accesses are 64-byte row segments.
-    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
-    const int slice = (warp - 2) >> 2;     // 0..3
-    float* stg = reinterpret_cast<float*>(smem + L::kBudget + L::kBarBytes) + (warp - 2) * 512;
-    const Epilogue& e = p.e;
-    const int rl_base = lane >> 2, j4 = lane & 3;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int batch = static_cast<int>(tile / tiles_per_batch);
-      const int rem = static_cast<int>(tile % tiles_per_batch);
-      const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
-      const int b0 = batch % p.nb0, b1 = batch / p.nb0;
-      ptx::mbar_wait(&tmem_full[as], aphase);
-      ptx::tc_fence_after();
-      const long obatch = static_cast<long>(b0) * e.obs0 + static_cast<long>(b1) * e.obs1;
-      const float* rbatch = e.resid ? e.resid + static_cast<long>(b0) * e.rbs0 + static_cast<long>(b1) * e.rbs1 : nullptr;
-      const float* bias = e.bias ? e.bias + static_cast<long>(b0) * e.bias_bs0 : nullptr;
-      const int row_base = m_blk * BLOCK_M + quarter * 32;
-      const bool rows_live = row_base < p.M;
-#pragma unroll 1
-      for (int c = slice; c < BLOCK_N / 16; c += 4) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + c * 16, v);
-        ptx::tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 16;
-        if (!rows_live || col0 >= p.N) continue;  // warp-uniform
-        // staging: row = lane (64 bytes), 16-byte chunk j at position j ^ ((lane >> 1) & 3): 4 wavefronts per access
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int col = col0 + j4 * 4;
-        const bool col_ok = col < p.N;   // N % 4 == 0 for PLAIN launches: a live column group is a whole float4
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && col_ok) bb = *reinterpret_cast<const float4*>(bias + col);
-        const f2 al = f2_splat(e.alpha);
-        const long ocol = obatch + col;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rl = i * 8 + rl_base;
-          const int row = row_base + rl;
-          if (row >= p.M || !col_ok) continue;
-          const float4 acc = *reinterpret_cast<const float4*>(stg + rl * 16 + ((j4 ^ ((rl >> 1) & 3)) << 2));
-          f2 a = f2_fma(f2_make(acc.x, acc.y), al, f2_make(bb.x, bb.y));
-          f2 b = f2_fma(f2_make(acc.z, acc.w), al, f2_make(bb.z, bb.w));
-          if (e.act == ACT_GELU) { a = gelu_erf2(a); b = gelu_erf2(b); }
-          else if (e.act == ACT_RELU) {
-            float u0, u1, u2, u3;
-            f2_get(a, u0, u1); f2_get(b, u2, u3);
-            a = f2_make(fmaxf(u0, 0.f), fmaxf(u1, 0.f)); b = f2_make(fmaxf(u2, 0.f), fmaxf(u3, 0.f));
-          }
-          if (rbatch) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rbatch + static_cast<long>(row) * e.ldr + col);
-            a = f2_add(a, f2_make(r4.x, r4.y));
-            b = f2_add(b, f2_make(r4.z, r4.w));
-          }
-          float f0, f1, f2_, f3;
-          f2_get(a, f0, f1); f2_get(b, f2_, f3);
-          const long o = ocol + static_cast<long>(row) * e.ldo;
-          if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + o) = make_float4(f0, f1, f2_, f3);
-          if (e.out_hi) {
-            uint32_t h01, l01, h23, l23;
-            split_pack_bf16x2(f0, f1, h01, l01);
-            split_pack_bf16x2(f2_, f3, h23, l23);
-            *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(h01, h23);
-            if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(l01, l23);
-          }
-        }
-        __syncwarp();  // staging block is reused by the next chunk
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================================================================== epilogue warps (8)
@@ -655,7 +564,7 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   if (c->gemm_grid_cap > 0) cap = std::min<long>(cap, c->gemm_grid_cap);
   if (c->small_grid_cap > 0 && p.num_tiles <= 2L * c->num_sms) cap = c->small_grid_cap;
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, cap));
-  kern<<<grid, Roles<PLAIN>::kThreadsT, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
 
 }  // namespace
@@ -677,6 +586,7 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
   p.m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   p.e = E;
+  if (c->lo_unused) p.e.out_lo = nullptr;  // single-pass bf16 ViT path: the consumers read only the hi planes
   bool vec = (E.ldo % 8 == 0) && (E.obs0 % 8 == 0) && (E.obs1 % 8 == 0);
   if (E.out_f32) vec = vec && (reinterpret_cast<uintptr_t>(E.out_f32) % 16 == 0);
   if (E.out_hi) vec = vec && (reinterpret_cast<uintptr_t>(E.out_hi) % 16 == 0);

@@ -26,10 +26,11 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 __device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, long off, const float4& y) {
-  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-  split_bf16(y.x, h0, l0); split_bf16(y.y, h1, l1); split_bf16(y.z, h2, l2); split_bf16(y.w, h3, l3);
-  *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-  if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+  uint32_t h01, l01, h23, l23;   // packed F2FP conversions (the scalar F2F.BF16 is an XU-pipe instruction)
+  split_pack2_bf16(y.x, y.y, h01, l01);
+  split_pack2_bf16(y.z, y.w, h23, l23);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(l01, l23);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,6 +599,7 @@ void gather_ln(Ctx* c, const float* src, long lds, const int* map, int nsrc, int
                long ldo_f32, bf16* out_hi, bf16* out_lo, long ldo_bf, bf16* out2_hi, bf16* out2_lo, float* out2_f32) {
   if (c->skipped(4)) return;
   if (rows == 0) return;
+  if (c->lo_unused) { out_lo = nullptr; out2_lo = nullptr; }  // single-pass bf16 ViT path: the lo planes are never read
   const int C = nsrc * Cs;
   ALM_REQUIRE((C % 128 == 0 || C == 192) && Cs % 4 == 0 && lds % 4 == 0, ALM_ERR_INVALID,
               "gather_ln: width must be a multiple of 128 (or 192)");

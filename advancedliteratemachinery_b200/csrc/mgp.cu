@@ -255,6 +255,13 @@ void mgp_forward(Ctx* c, const float* img, int B, float* attn_out, float* char_l
     ws.release(mk);
   }
   const bool fused_attn = c->attn_impl == 0;
+  // single-pass bf16 with the fused attention: every consumer (GEMM, attention) reads only the hi planes, so the
+  // producers skip computing and writing the lo halves (half of the operand-plane traffic of the ViT)
+  struct LoGuard {
+    Ctx* c;
+    ~LoGuard() { c->lo_unused = false; }
+  } lo_guard{c};
+  c->lo_unused = (c->nsplit == 1) && fused_attn;
   SB ln = sb(c, R * D);
   SB qk{nullptr, nullptr}, vt{nullptr, nullptr}, P{nullptr, nullptr}, qkv{nullptr, nullptr};
   float* S = nullptr;

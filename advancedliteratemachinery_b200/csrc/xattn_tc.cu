@@ -17,8 +17,10 @@
 //
 // One kernel serves the point loop (one query per image: HBM-bound, the MMA rows are nearly all padding but the tensor
 // pipe is otherwise idle) and the polygon / recognition loops (64 queries per image: the mma.sync kernel was
-// MMA-latency bound at 46 % of the HMMA pipe).  Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps
-// 2..5 softmax / fold / merge.
+// MMA-latency bound at 46 % of the HMMA pipe).  Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps
+// 2..17 softmax / fold / merge: FOUR threads per query row (lane quarter = warp % 4 selects the 32 rows a warp may touch in
+// tensor memory, key group = (warp - 2) / 4 selects 32 of the block's 128 keys and 16 of the 64 output dims), so the
+// per-block softmax is a quarter of a row's work per thread and a single tensor-memory round trip.
 #include <algorithm>
 
 #include "omni.h"
@@ -28,7 +30,7 @@ namespace alm {
 
 namespace {
 
-constexpr int XT_THREADS = 192;
+constexpr int XT_THREADS = 576;            // warp 0 TMA, warp 1 MMA, warps 2..17 softmax: lane quarter = w % 4, key group = (w - 2) / 4
 constexpr int XT_KB = 128;               // keys per block
 constexpr int XT_TILE = XT_KB * 128;     // bytes of one 128 x 64 bf16 operand tile
 constexpr int XT_STAGES = 3;
@@ -40,7 +42,8 @@ struct XtSmem {
   static constexpr int kStage = 2 * NP * XT_TILE;          // K and V of every plane
   static constexpr int kQ = XT_STAGES * kStage;
   static constexpr int kBar = kQ + NP * XT_TILE;
-  static constexpr int kTotal = kBar + 256 + 1024;
+  static constexpr int kXch = kBar + 256;                  // per-row exchange between the four key groups: [4][128] floats
+  static constexpr int kTotal = kXch + 4 * 128 * 4 + 1024;
 };
 
 struct XtParams {
@@ -96,11 +99,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_full[s], 4);
+      ptx::mbar_init(&p_full[s], 16);
       ptx::mbar_init(&o_full[s], 1);
-      ptx::mbar_init(&o_empty[s], 4);
+      ptx::mbar_init(&o_empty[s], 16);
     }
-    ptx::mbar_init(q_ready, 4);
+    ptx::mbar_init(q_ready, 16);
     ptx::mbar_init(q_free, 1);
     ptx::fence_mbar_init();
   }
@@ -201,10 +204,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
     }
   } else {
     // ================================================================================= softmax / fold / merge warps
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, cg = (warp - 2) >> 2;   // lane quarter, key / output-dim group
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
     const int r = quarter * 32 + lane;                 // query row of the 128-row tile
-    const int tid4 = threadIdx.x - 64;                 // 0..127 among the softmax warps
+    const int tid16 = threadIdx.x - 64;                // 0..511 among the softmax warps
+    float* xch = reinterpret_cast<float*>(smem + L::kXch);   // [4 key groups][128 rows]
     uint32_t s_phase[2] = {0, 0}, o_phase[2] = {0, 0}, qf_phase = 0;
     int sb = 0;
     bool first_segment = true;
@@ -226,7 +230,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
         qf_phase ^= 1;
       }
       first_segment = false;
-      for (int i = tid4; i < 128 * 8; i += 128) {
+      for (int i = tid16; i < 128 * 8; i += 512) {
         const int row = i >> 3, ch = i & 7;
         uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
         if (q0 + row < p.Ncap) {
@@ -234,16 +238,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
           if (p.q_f32) {
             const float4 a = *reinterpret_cast<const float4*>(p.q_f32 + src);
             const float4 c = *reinterpret_cast<const float4*>(p.q_f32 + src + 4);
-            const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
             uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              bf16 h0, l0, h1, l1;
-              split_bf16(f[2 * e], h0, l0);
-              split_bf16(f[2 * e + 1], h1, l1);
-              hh[e] = pack_bf16(h0, h1);
-              ll[e] = pack_bf16(l0, l1);
-            }
+            split_pack2_bf16(a.x, a.y, hh[0], ll[0]);
+            split_pack2_bf16(a.z, a.w, hh[1], ll[1]);
+            split_pack2_bf16(c.x, c.y, hh[2], ll[2]);
+            split_pack2_bf16(c.z, c.w, hh[3], ll[3]);
             vh = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             vl = make_uint4(ll[0], ll[1], ll[2], ll[3]);
           } else {
@@ -259,16 +258,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(q_ready);
 
-      // ---- running flash statistics of this thread's row, O in registers
+      // ---- running flash statistics: m is the row's (all four threads agree), l and O are this thread's share
       float m_run = -INFINITY, l_run = 0.f;
-      float o_run[64];
+      float o_run[16];
 #pragma unroll
-      for (int d = 0; d < 64; ++d) o_run[d] = 0.f;
+      for (int d = 0; d < 16; ++d) o_run[d] = 0.f;
       float m_pend = -INFINITY, l_pend = 0.f;   // block statistics of the block whose O_b is still in tensor memory
       const uint8_t* kpm = p.kpm ? p.kpm + static_cast<long>(img) * p.M : nullptr;
 
       auto fold = [&](int buf) {
-        // (m, l, O) <- flash merge of the running state with block (m_pend, l_pend, O_b)
+        // (m, l, O) <- flash merge of the running state with block (m_pend, l_pend, O_b); this thread folds 16 output dims
         ptx::mbar_wait(&o_full[buf], o_phase[buf]);
         o_phase[buf] ^= 1;
         ptx::tc_fence_after();
@@ -276,14 +275,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
           const float m_new = fmaxf(m_run, m_pend);
           const float a = m_run == -INFINITY ? 0.f : xt_ex2((m_run - m_new) * p.scale_log2e);
           const float c = m_pend == -INFINITY ? 0.f : xt_ex2((m_pend - m_new) * p.scale_log2e);
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(lane_addr + O_COL[buf] + cg * 16, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld_32x16(lane_addr + O_COL[buf] + c0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o_run[c0 + j] = fmaf(o_run[c0 + j], a, __uint_as_float(v[j]) * c);
-          }
+          for (int j = 0; j < 16; ++j) o_run[j] = fmaf(o_run[j], a, __uint_as_float(v[j]) * c);
           l_run = fmaf(l_run, a, l_pend * c);
           m_run = m_new;
         }
@@ -294,49 +290,47 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
 
       for (int i = 0; i < n; ++i) {
         const int buf = (sb + i) & 1;
-        const int key0 = (kb0 + i) * XT_KB;
+        const int key0 = (kb0 + i) * XT_KB + cg * 32;   // this thread's 32 keys of the block
         ptx::mbar_wait(&s_full[buf], s_phase[buf]);
         s_phase[buf] ^= 1;
         ptx::tc_fence_after();
-        float m_blk = -INFINITY, l_blk = 0.f;
+        uint32_t v[32];
+        uint32_t mbits = 0xffffffffu;
+        float m_mine = -INFINITY;
         if (warp_live) {
-          // key-padding mask of the block as 4 x 32 bits, fetched once (one memory round trip, no alignment assumption):
-          // lane L looks at keys L, L + 32, L + 64, L + 96 of the block; a ballot hands every lane all 128 bits
-          uint32_t mw[4];
+          ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + cg * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + cg * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          // key-padding mask of this thread's 32 keys as one ballot (no alignment assumption on the mask rows)
+          const int key = key0 + lane;
+          mbits = __ballot_sync(0xffffffffu, key >= p.M || (kpm != nullptr && kpm[key < p.M ? key : 0] != 0));
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int key = key0 + 32 * j + lane;
-            const bool masked = key >= p.M || (kpm != nullptr && kpm[key < p.M ? key : 0] != 0);
-            mw[j] = __ballot_sync(0xffffffffu, masked);
-          }
-          // pass 1: block maximum over the unmasked keys
-#pragma unroll
-          for (int c0 = 0; c0 < XT_KB; c0 += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + c0, v);
-            ptx::tmem_ld_wait();
-            const uint32_t bits = mw[c0 >> 5] >> (c0 & 31);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (!((bits >> j) & 1u)) m_blk = fmaxf(m_blk, __uint_as_float(v[j]));
-          }
-          // pass 2: p = 2^((s - m_b) c), block sum, bf16 (hi, lo) pairs back into tensor memory
+          for (int j = 0; j < 32; ++j)
+            if (!((mbits >> j) & 1u)) m_mine = fmaxf(m_mine, __uint_as_float(v[j]));
+        }
+        // the four threads of a row agree on the block maximum; the barrier also orders "every thread has read its S
+        // columns" before anybody overwrites the S buffer with the low halves of P
+        xch[cg * 128 + r] = m_mine;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float m_blk = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
+        asm volatile("bar.sync 2, 512;" ::: "memory");   // xch may be rewritten for the next block only after all reads
+        float l_blk = 0.f;
+        if (warp_live) {
           const float mc = m_blk == -INFINITY ? 0.f : m_blk * p.scale_log2e;
+          const uint32_t bits = mbits | (live ? 0u : 0xffffffffu);
 #pragma unroll
-          for (int c0 = 0; c0 < XT_KB; c0 += 16) {
-            uint32_t v[16], ph[8], pl[8];
-            ptx::tmem_ld_32x16(lane_addr + S_COL[buf] + c0, v);
-            ptx::tmem_ld_wait();
-            const uint32_t bits = (mw[c0 >> 5] >> (c0 & 31)) | (live ? 0u : 0xffffu);
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t ph[8], pl[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
+            for (int jj = 0; jj < 16; jj += 2) {
+              const int j = hf * 16 + jj;
               const float e0 = ((bits >> j) & 1u) ? 0.f : xt_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc));
               const float e1 = ((bits >> (j + 1)) & 1u) ? 0.f : xt_ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc));
               l_blk += e0 + e1;
-              split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
+              split_pack2_bf16(e0, e1, ph[jj >> 1], pl[jj >> 1]);
             }
-            ptx::tmem_st_32x8(lane_addr + P_COL[buf] + (c0 >> 1), ph);
-            if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + S_COL[buf] + (c0 >> 1), pl);   // behind this thread's read pointer
+            ptx::tmem_st_32x8(lane_addr + P_COL[buf] + cg * 16 + hf * 8, ph);
+            if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + S_COL[buf] + cg * 16 + hf * 8, pl);   // S is fully consumed (barrier above)
           }
           ptx::tmem_st_wait();
         }
@@ -351,44 +345,50 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
       fold((sb + n - 1) & 1);
       sb = (sb + n) & 1;
 
+      // ---- the row sum over the four key groups
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      xch[cg * 128 + r] = l_run;
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      const float l_row = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+
       // ---- result of the segment: final output when this CTA covered the whole pair, else a partial for the merge
-      const long orow = (static_cast<long>(img) * p.Ncap + q0 + r) * 512 + h * 64;
-      auto write_row = [&](const float (&o)[64], float inv) {
+      const long orow = (static_cast<long>(img) * p.Ncap + q0 + r) * 512 + h * 64 + cg * 16;
+      auto write16 = [&](const float (&o)[16], float inv) {
+        float x[16];
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 8) {
-          float x[8];
+        for (int j = 0; j < 16; ++j) x[j] = o[j] * inv;
+        if (p.out_f32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = o[c0 + j] * inv;
-          if (p.out_f32) {
-            *reinterpret_cast<float4*>(p.out_f32 + orow + c0) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(p.out_f32 + orow + c0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-          }
-          if (p.out_hi) {
-            uint32_t hh[4], ll[4];
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p.out_f32 + orow + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+        if (p.out_hi) {
+          uint32_t hh[8], ll[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split_pack2_bf16(x[2 * j], x[2 * j + 1], hh[j], ll[j]);
-            *reinterpret_cast<uint4*>(p.out_hi + orow + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + orow + c0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          for (int j = 0; j < 8; ++j) split_pack2_bf16(x[2 * j], x[2 * j + 1], hh[j], ll[j]);
+          *reinterpret_cast<uint4*>(p.out_hi + orow) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(p.out_hi + orow + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+          if (p.out_lo) {
+            *reinterpret_cast<uint4*>(p.out_lo + orow) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + orow + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
           }
         }
       };
       if (gs == 1) {
-        if (live) write_row(o_run, 1.0f / l_run);
+        if (live) write16(o_run, 1.0f / l_row);
         continue;
       }
       float* part = p.partial + ((static_cast<long>(pair) * p.max_parts + split) * 128 + r) * XT_PART;
       if (live) {
-        part[0] = m_run;
-        part[1] = l_run;
+        if (cg == 0) { part[0] = m_run; part[1] = l_row; }
 #pragma unroll
-        for (int d = 0; d < 64; d += 2) *reinterpret_cast<float2*>(part + 2 + d) = make_float2(o_run[d], o_run[d + 1]);
+        for (int d = 0; d < 16; d += 2) *reinterpret_cast<float2*>(part + 2 + cg * 16 + d) = make_float2(o_run[d], o_run[d + 1]);
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid4 == 0) *last_flag = (atomicAdd(&p.counters[pair], 1) == gs - 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tid16 == 0) *last_flag = (atomicAdd(&p.counters[pair], 1) == gs - 1);
+      asm volatile("bar.sync 2, 512;" ::: "memory");
       const bool last = *last_flag != 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone has read the flag before it can be rewritten
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // everyone has read the flag before it can be rewritten
       if (!last) continue;
       __threadfence();
       if (live) {
@@ -396,24 +396,24 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
         const long sstride = 128L * XT_PART;
         float mm = -INFINITY;
         for (int s_ = 0; s_ < gs; ++s_) mm = fmaxf(mm, base[s_ * sstride]);
-        float ltot = 0.f, acc[64];
+        float ltot = 0.f, acc[16];
 #pragma unroll
-        for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+        for (int d = 0; d < 16; ++d) acc[d] = 0.f;
         for (int s_ = 0; s_ < gs; ++s_) {
           const float* ps = base + s_ * sstride;
           const float ms = ps[0];
           const float wgt = ms == -INFINITY ? 0.f : xt_ex2((ms - mm) * p.scale_log2e);
           ltot = fmaf(wgt, ps[1], ltot);
 #pragma unroll
-          for (int d = 0; d < 64; d += 2) {
-            const float2 v = *reinterpret_cast<const float2*>(ps + 2 + d);
-            acc[d] = fmaf(wgt, v.x, acc[d]);
-            acc[d + 1] = fmaf(wgt, v.y, acc[d + 1]);
+          for (int d = 0; d < 16; d += 2) {
+            const float2 vv = *reinterpret_cast<const float2*>(ps + 2 + cg * 16 + d);
+            acc[d] = fmaf(wgt, vv.x, acc[d]);
+            acc[d + 1] = fmaf(wgt, vv.y, acc[d + 1]);
           }
         }
-        write_row(acc, 1.0f / ltot);
+        write16(acc, 1.0f / ltot);
       }
-      if (tid4 == 0) p.counters[pair] = 0;   // ready for the next launch (graph replay)
+      if (tid16 == 0) p.counters[pair] = 0;   // ready for the next launch (graph replay)
     }
   }
 
