@@ -12,7 +12,7 @@
 // are loaded once, then the ceil(T/128) query tiles run through
 //     warp 0      TMA producer (one elected lane)
 //     warp 1      tcgen05.mma issuer (one elected lane)
-//     warps 2..5  softmax + output epilogue: thread = query row (the TMEM lane its warp may access)
+//     warps 2..9  softmax + output epilogue: two threads per query row (lane quarter = warp % 4, key half = (warp-2)/4)
 // with mbarrier hand-offs: S(i+1) is issued right behind P(i) V, so it runs while the epilogue of tile i drains O.
 // TMEM map (512 columns): S [0, TK) fp32; P_hi [TK, TK + TK/2) bf16 pairs; O [TK + TK/2, +64) fp32; in split mode the low
 // halves P_lo overwrite S in place, behind the read pointer of the (single) thread that owns the row.
@@ -28,7 +28,7 @@ namespace alm {
 
 namespace {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 softmax: lane quarter = w % 4, key half = (w - 2) / 4
 constexpr int AT_TKMAX = 272;             // keys padded to a multiple of 16 (UMMA N granularity at M = 128)
 constexpr int AT_BOX = 136;               // rows of one TMA box: two boxes cover the keys, one covers a 128-row Q tile
 constexpr int AT_BOXB = AT_BOX * 128;     // 17 408 bytes, a multiple of the 1024-byte swizzle atom
@@ -42,7 +42,8 @@ struct AtSmem {
   static constexpr int kV = kK + NP * AT_KVB;
   static constexpr int kQ = kV + NP * AT_KVB;
   static constexpr int kBar = kQ + AT_QSTAGES * NP * AT_BOXB;
-  static constexpr int kTotal = kBar + 256 + 1024;  // + alignment slack
+  static constexpr int kXch = kBar + 256;           // per-row exchange between the two key halves: [2][128] floats
+  static constexpr int kTotal = kXch + 1024 + 1024;  // + alignment slack
 };
 
 struct AtParams {
@@ -95,9 +96,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       ptx::mbar_init(&q_empty[s], 1);
     }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 4);   // one arrival per softmax warp
+    ptx::mbar_init(p_full, 8);   // one arrival per softmax warp
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_empty, 4);
+    ptx::mbar_init(o_empty, 8);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -185,11 +186,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         if (ptx::elect_one()) {
           const int ksteps = TK / 16;
 #pragma unroll
+          const int n0 = (ksteps + 1) / 2;   // key chunks of the first softmax half (see the softmax warps)
           for (int pass = 0; pass < NSPLIT; ++pass) {
-            const uint32_t pa = tmem + (pass == 1 ? PLO_COL : P_COL);
             const uint32_t vb = v_base + (pass == 2 ? AT_KVB : 0);
-            for (int j = 0; j < ksteps; ++j)
-              ptx::umma_bf16_ts(tmem + O_COL, pa + j * 8, ptx::make_kmajor_sw128_desc(vb + j * 2048), idesc_pv, (pass | j) != 0);
+            for (int j = 0; j < ksteps; ++j) {
+              // hi halves of P: their own region, 8 columns per 16 keys.  lo halves: in place over S, each softmax half
+              // inside the S columns it owns (half 0 at column 8 j, half 1 at 16 n0 + 8 (j - n0))
+              const uint32_t pa = pass == 1 ? tmem + PLO_COL + (j < n0 ? j * 8 : 16 * n0 + (j - n0) * 8) : tmem + P_COL + j * 8;
+              ptx::umma_bf16_ts(tmem + O_COL, pa, ptx::make_kmajor_sw128_desc(vb + j * 2048), idesc_pv, (pass | j) != 0);
+            }
           }
           ptx::umma_commit(o_full);
           if (i == p.tiles - 1) ptx::umma_commit(kv_empty);  // K / V of this item are free once these MMAs retire
@@ -199,62 +204,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     }
   } else {
     // ================================================================================= softmax + epilogue warps
-    const int quarter = warp & 3;  // the TMEM lanes [32*quarter, +32) this warp may access
+    // TWO threads per query row (the per-tile softmax is the longest link of the tile's dependency chain): warps w and
+    // w + 4 share a lane quarter; half 0 owns the first n0 16-key chunks of the row, half 1 the rest; they agree on the row
+    // maximum and the row sum through shared memory; the epilogue splits the 64 output dims the same way.
+    const int quarter = warp & 3, hf = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + (uint32_t(quarter * 32) << 16);
+    float* xch = reinterpret_cast<float*>(smem + L::kXch);   // [2][128]
+    const int nch = TK / 16, n0 = (nch + 1) / 2;
+    const int c_lo = hf ? n0 : 0, c_hi = hf ? nch : n0;
+    const uint32_t plo_base = PLO_COL + (hf ? 16 * n0 : 0);  // this half's in-place region for the lo halves of P
     uint32_t s_phase = 0, o_phase = 0;
     for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int b = static_cast<int>(it / p.H), h = static_cast<int>(it % p.H);
       for (int i = 0; i < p.tiles; ++i) {
-        const int row = i * 128 + quarter * 32 + lane;
+        const int r = quarter * 32 + lane;
+        const int row = i * 128 + r;
         const bool warp_live = i * 128 + quarter * 32 < p.T;
         ptx::mbar_wait(s_full, s_phase);
         s_phase ^= 1;
         ptx::tc_fence_after();
-        float l = 1.0f;
+        // pass 1: maximum over this half's live keys
+        float m = -INFINITY;
         if (warp_live) {
-          // pass 1: row maximum over the live keys
-          float m = -INFINITY;
-          for (int c0 = 0; c0 < TK; c0 += 16) {
+          for (int c = c_lo; c < c_hi; ++c) {
             uint32_t v[16];
-            ptx::tmem_ld_32x16(lane_addr + S_COL + c0, v);
+            ptx::tmem_ld_32x16(lane_addr + S_COL + c * 16, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+              if (c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
           }
-          // pass 2: p = 2^((s - m) * c); row sum; bf16 (hi, lo) pairs back into tensor memory
+        }
+        xch[hf * 128 + r] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(xch[r], xch[128 + r]);
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // both halves have read the maxima before xch is reused
+        // pass 2: p = 2^((s - m) * c); partial row sum; bf16 (hi, lo) pairs back into tensor memory
+        float l = 0.f;
+        if (warp_live) {
           const float mc = m * p.scale_log2e;
-          l = 0.f;
-          for (int c0 = 0; c0 < TK; c0 += 16) {
+          for (int c = c_lo; c < c_hi; ++c) {
             uint32_t v[16], ph[8], pl[8];
-            ptx::tmem_ld_32x16(lane_addr + S_COL + c0, v);
+            ptx::tmem_ld_32x16(lane_addr + S_COL + c * 16, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float e0 = c0 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc)) : 0.f;
-              float e1 = c0 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc)) : 0.f;
+              float e0 = c * 16 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc)) : 0.f;
+              float e1 = c * 16 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc)) : 0.f;
               l += e0 + e1;
               split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
             }
-            ptx::tmem_st_32x8(lane_addr + P_COL + (c0 >> 1), ph);
-            if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + PLO_COL + (c0 >> 1), pl);  // behind this thread's read pointer
+            ptx::tmem_st_32x8(lane_addr + P_COL + c * 8, ph);
+            if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + plo_base + (c - c_lo) * 8, pl);  // behind this thread's read pointer
           }
           ptx::tmem_st_wait();
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_full);
-        // ---- epilogue: O / l -> split bf16 planes (operand of the projection GEMM), token-major [B*T, D]
+        // row sum over both halves
+        xch[hf * 128 + r] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l = xch[r] + xch[128 + r];
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        // ---- epilogue: O / l -> split bf16 planes (operand of the projection GEMM), token-major [B*T, D]; this half
+        //      writes output dims [32 hf, 32 hf + 32)
         ptx::mbar_wait(o_full, o_phase);
         o_phase ^= 1;
         ptx::tc_fence_after();
         if (warp_live) {
           const float inv = 1.0f / l;
-          const long orow = (static_cast<long>(b) * p.T + row) * p.ldo + h * 64;
+          const long orow = (static_cast<long>(b) * p.T + row) * p.ldo + h * 64 + hf * 32;
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
+          for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t v[16];
-            ptx::tmem_ld_32x16(lane_addr + O_COL + c0, v);
+            ptx::tmem_ld_32x16(lane_addr + O_COL + hf * 32 + c0, v);
             ptx::tmem_ld_wait();
             if (row < p.T) {
               uint32_t hh[8], ll[8];

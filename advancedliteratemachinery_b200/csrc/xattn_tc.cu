@@ -43,7 +43,7 @@ struct XtSmem {
   static constexpr int kQ = XT_STAGES * kStage;
   static constexpr int kBar = kQ + NP * XT_TILE;
   static constexpr int kXch = kBar + 256;                  // per-row exchange between the four key groups: [4][128] floats
-  static constexpr int kTotal = kXch + 4 * 128 * 4 + 1024;
+  static constexpr int kTotal = kXch + 4 * 128 * 4;        // 231 680 B: the dynamic array is declared 1024-byte aligned
 };
 
 struct XtParams {
@@ -72,8 +72,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_con
                      const __grid_constant__ CUtensorMap tm_vh, const __grid_constant__ CUtensorMap tm_vl, const XtParams p) {
   using L = XtSmem<NSPLIT>;
   constexpr int NP = L::NP;
-  extern __shared__ uint8_t xt_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xt_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t xt_raw[];   // no static shared memory in this kernel: the window starts aligned
+  uint8_t* smem = xt_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();     // the 128-byte swizzle atoms need it; never expected to fire
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint64_t* kv_full = bars + 0;     // [3]
   uint64_t* kv_empty = bars + 3;    // [3]
