@@ -185,7 +185,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const int ksteps = TK / 16;
-#pragma unroll
           const int n0 = (ksteps + 1) / 2;   // key chunks of the first softmax half (see the softmax warps)
           for (int pass = 0; pass < NSPLIT; ++pass) {
             const uint32_t vb = v_base + (pass == 2 ? AT_KVB : 0);

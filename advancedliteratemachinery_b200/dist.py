@@ -9,8 +9,9 @@ packing, padding and page re-ordering logic is transport-independent and is exer
 (tests/test_dist_cpu.py)."""
 from __future__ import annotations
 
+import threading
 from collections import OrderedDict
-from typing import List, Optional
+from typing import Callable, List, Optional
 
 import numpy as np
 import torch
@@ -24,6 +25,54 @@ def shard_pages(n_pages: int, rank: int, world: int) -> List[int]:
 
 def pages_per_rank(n_pages: int, world: int) -> int:
     return (n_pages + world - 1) // world
+
+
+# ------------------------------------------------------------------------------------------------ ordering
+class CollectiveOrder:
+    """Issue the collectives of several execution contexts (one NCCL communicator each, one host thread each) in ONE
+    global order that is the same on every rank.
+
+    NCCL's rule for several communicators in a process: their operations must be issued in the same order on all ranks.
+    A gather kernel spins on the device until its peers arrive; if rank 0 issued context A's gather first and rank 1
+    context B's, each rank would hold a spinning kernel (and possibly a cudaMalloc / hardware-queue slot behind it) that
+    only the OTHER context of the peer can release -- a deadlock.  Work is numbered by a `ticket` that every rank derives
+    the same way (the global step index); `run(ticket, fn)` blocks until all lower tickets have finished, then runs `fn`
+    (the synchronous gather call).  A failure in any ticket releases the waiters with an error instead of hanging them."""
+
+    def __init__(self, timeout_s: float = 300.0):
+        self._cv = threading.Condition()
+        self._next = 0
+        self._failed: Optional[BaseException] = None
+        self._timeout = timeout_s
+
+    def reset(self, first_ticket: int = 0) -> None:
+        with self._cv:
+            self._next, self._failed = first_ticket, None
+
+    def fail(self, exc: BaseException) -> None:
+        with self._cv:
+            if self._failed is None:
+                self._failed = exc
+            self._cv.notify_all()
+
+    def run(self, ticket: int, fn: Callable):
+        with self._cv:
+            ok = self._cv.wait_for(lambda: self._failed is not None or self._next == ticket, timeout=self._timeout)
+            if self._failed is not None:
+                raise RuntimeError(f'collective {ticket} abandoned: an earlier one failed') from self._failed
+            if not ok:
+                self._failed = TimeoutError(f'collective {ticket} waited {self._timeout:.0f} s for ticket {self._next}')
+                self._cv.notify_all()
+                raise self._failed
+        try:
+            out = fn()
+        except BaseException as e:
+            self.fail(e)
+            raise
+        with self._cv:
+            self._next = ticket + 1
+            self._cv.notify_all()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ weights

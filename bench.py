@@ -318,6 +318,8 @@ def main():
                     'their launch gaps.  0 = the workload default')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
     ap.add_argument('--ref-budget-s', type=float, default=330.0, help='reference arm: stop adding timed steps past this')
+    ap.add_argument('--watchdog-s', type=float, default=600.0, help='a timed phase that takes longer dumps every host '
+                    'thread\'s stack to stderr and exits non-zero (a hung collective must not burn the GPU box)')
     ap.add_argument('--cpu-child', nargs=3, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_child:
@@ -325,11 +327,12 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    import faulthandler
     import numpy as np
     import torch
     import torch.distributed as dist
     from advancedliteratemachinery_b200 import MGPSTRB200, NestedTensor, OmniParserB200, OmniVocab, _lib
-    from advancedliteratemachinery_b200.dist import gather_sequences, init_comm, load_weights_broadcast
+    from advancedliteratemachinery_b200.dist import CollectiveOrder, gather_sequences, init_comm, load_weights_broadcast
     from advancedliteratemachinery_b200 import synthetic as W  # synthetic checkpoint (data only)
 
     torch.set_grad_enabled(False)
@@ -405,10 +408,16 @@ def main():
         models[j].encode(x, None)
         return models[j].decode_points() if w['points_only'] else models[j].decode()
 
-    def gather(j, out):
-        """ONE all-gather of the decoded sequences of this step over the context's NCCL communicator."""
+    order = CollectiveOrder()
+
+    def gather(j, out, s):
+        """ONE all-gather of the decoded sequences of step `s` over the context's NCCL communicator, issued in step order
+        (the same on every rank: several communicators may only be used in one global order, dist.CollectiveOrder)."""
         if world == 1:
             return None
+        return order.run(s, lambda: gather_now(j, out))
+
+    def gather_now(j, out):
         if is_mgp:
             ids, prob = out
             buf = np.concatenate([ids.numpy().reshape(-1), prob.numpy().view(np.int32).reshape(-1)])
@@ -422,22 +431,28 @@ def main():
             return ctxs[j].gather(buf, world)
         return gather_sequences(out, vocab, n_pages=world * B, ctx=ctxs[j])
 
-    def step_resident(j):
+    def step_resident(j, s):
         out = run_model(j, dev_in)
-        return out, gather(j, out)
+        return out, gather(j, out, s)
 
-    def step_e2e(j):
+    def step_e2e(j, s):
         out = run_model(j, host_in)
-        return out, gather(j, out)
+        return out, gather(j, out, s)
 
     def run_steps(fn, steps):
         """`steps` batches; step s runs on context s % C (static, so that the per-context collectives line up across
         ranks).  One host thread per context: the C calls release the GIL, the per-context streams overlap on the device."""
         last = [None] * C_
+        errors = []
+        order.reset(0)
 
         def worker(j):
-            for _ in range(j, steps, C_):
-                last[j] = fn(j)
+            try:
+                for s in range(j, steps, C_):
+                    last[j] = fn(j, s)
+            except BaseException as e:       # release the other contexts' threads instead of leaving them in a collective
+                errors.append(e)
+                order.fail(e)
         if C_ == 1:
             worker(0)
         else:
@@ -446,11 +461,21 @@ def main():
                 t.start()
             for t in ts:
                 t.join()
+        if errors:
+            raise errors[0]
         return last
 
     def timed(fn, steps, warmup):
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
+        try:
+            return timed_(fn, steps, warmup)
+        finally:
+            faulthandler.cancel_dump_traceback_later()
+
+    def timed_(fn, steps, warmup):
+        order.reset(0)
         for j in range(C_):          # every context runs once (graph capture, descriptor caches) ...
-            fn(j)
+            fn(j, j)
         run_steps(fn, warmup)        # ... then `warmup` untimed steps through the scheduler
         torch.cuda.synchronize()
         if world > 1:
@@ -514,11 +539,12 @@ def main():
     achieved = 2.0 * M_ * N_ * K_ / (gemm_ms * 1e-3) / 1e12
     torch.cuda.synchronize()
     phase_ms, enc_ms = None, None
-    step_resident(0)                       # one isolated step: device times without cross-batch contention
+    order.reset(0)
+    step_resident(0, 0)                    # one isolated step: device times without cross-batch contention
     if not is_mgp:
         phase_ms = ctx.omni_last_timing()
     ctx.set_option('profile_gemm', 1)
-    step_resident(0)
+    step_resident(0, 1)
     g_ms, g_flops, g_n = ctx.profile_read()
     ctx.set_option('profile_gemm', 0)
     torch.cuda.synchronize()

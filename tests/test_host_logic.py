@@ -70,3 +70,38 @@ def test_xattn_runs_partition_the_work_and_bound_the_partials():
             assert 1 <= last - first + 1 <= max_parts      # partial slots reserved per pair suffice
             for cta in range(first, last + 1):              # every CTA in first..last owns a block of this pair
                 assert any(seen[b] == cta for b in range(p * nkb, (p + 1) * nkb))
+
+
+def test_collective_order_runs_tickets_in_order_and_releases_waiters_on_failure():
+    """dist.CollectiveOrder: the gathers of several contexts' host threads are issued in ticket (global step) order
+    whatever order the threads arrive in; a failing ticket releases the later ones with an error instead of hanging."""
+    import threading
+    import time
+    import pytest
+    from advancedliteratemachinery_b200.dist import CollectiveOrder
+    order, seen = CollectiveOrder(timeout_s=20.0), []
+
+    def worker(t, delay):
+        time.sleep(delay)
+        order.run(t, lambda: seen.append(t))
+    ts = [threading.Thread(target=worker, args=(t, d)) for t, d in ((3, 0.0), (1, 0.05), (0, 0.15), (2, 0.1))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert seen == [0, 1, 2, 3]
+
+    order.reset(0)
+    errs = []
+
+    def waiter():
+        try:
+            order.run(1, lambda: None)
+        except RuntimeError as e:
+            errs.append(e)
+    w = threading.Thread(target=waiter)
+    w.start()
+    with pytest.raises(ValueError):
+        order.run(0, lambda: (_ for _ in ()).throw(ValueError('boom')))
+    w.join(10)
+    assert not w.is_alive() and len(errs) == 1
