@@ -92,6 +92,8 @@ struct Epilogue {
   bf16* out_hi = nullptr;
   bf16* out_lo = nullptr;
   long ldo = 0, obs0 = 0, obs1 = 0;  // fp32 and bf16 outputs share geometry
+  int col_group = 0;                 // > 0: output column c goes to (c / col_group) * col_group_stride + c % col_group
+  long col_group_stride = 0;         //      (head-major K/V caches written by ONE wide GEMM; col_group % 4 == 0)
   const float* bias = nullptr;
   int bias_mode = BIAS_NONE;
   long bias_bs0 = 0;  // per-batch(b0) bias stride

@@ -366,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                          : make_float4(0.f, 0.f, 0.f, 0.f);
           // phase 2: straight-line math + stores; the option checks are hoisted into one switch per chunk
           const int kind = e.act * 4 + (e.out_f32 ? 1 : 0) + (e.out_hi ? 2 : 0);
-          const long ocol = obatch + col;
+          const long ocol = obatch + (e.col_group ? static_cast<long>(col / e.col_group) * e.col_group_stride + col % e.col_group : col);
           switch (kind) {
 #define ALM_EPI_CASE(ACTV, F32V, SPLV)                                                                         \
   case (ACTV) * 4 + (F32V) + 2 * (SPLV):                                                                        \
@@ -383,7 +383,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (orow[i] < 0) continue;
-            const long o = obatch + static_cast<long>(orow[i]) * e.ldo + col;
+            const long o = obatch + static_cast<long>(orow[i]) * e.ldo +
+                           (e.col_group ? static_cast<long>(col / e.col_group) * e.col_group_stride + col % e.col_group : col);
             const float f[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -475,7 +476,8 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
   if (e.act == ACT_GELU) x = gelu_erf(x);
   else if (e.act == ACT_RELU) x = fmaxf(x, 0.f);
   if (e.resid) x += e.resid[b0 * e.rbs0 + b1 * e.rbs1 + rrow * e.ldr + col];
-  const long o = b0 * e.obs0 + b1 * e.obs1 + orow * e.ldo + col;
+  const long o = b0 * e.obs0 + b1 * e.obs1 + orow * e.ldo +
+                 (e.col_group ? static_cast<long>(col / e.col_group) * e.col_group_stride + col % e.col_group : col);
   if (e.out_f32) e.out_f32[o] = x;
   if (e.out_hi) {
     bf16 h, l;
@@ -588,6 +590,8 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
   p.e = E;
   if (c->lo_unused) p.e.out_lo = nullptr;  // single-pass bf16 ViT path: the consumers read only the hi planes
   bool vec = (E.ldo % 8 == 0) && (E.obs0 % 8 == 0) && (E.obs1 % 8 == 0);
+  ALM_REQUIRE(E.col_group == 0 || (E.col_group % 4 == 0 && E.col_group_stride % 8 == 0 && !E.resid), ALM_ERR_INVALID,
+              "gemm: column-group scatter needs groups of 4k columns and no residual");
   if (E.out_f32) vec = vec && (reinterpret_cast<uintptr_t>(E.out_f32) % 16 == 0);
   if (E.out_hi) vec = vec && (reinterpret_cast<uintptr_t>(E.out_hi) % 16 == 0);
   if (E.out_lo) vec = vec && (reinterpret_cast<uintptr_t>(E.out_lo) % 16 == 0);

@@ -383,11 +383,12 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     Operand a = act_op(memp.hi, memp.lo, m->M, 512, 512);
     a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
     Operand w = m->ca_k_all.w.op();
-    w.rows = 64; w.nb0 = 32 * c->kv_decoders; w.bs0 = static_cast<long>(64) * 512;  // (decoder, layer, head) slices
+    w.rows = 512; w.nb0 = 4 * c->kv_decoders; w.bs0 = static_cast<long>(512) * 512;  // (decoder, layer) slices, 8 heads wide
     Epilogue e;
     e.out_hi = m->kc_hi; e.out_lo = m->kc_lo; e.ldo = 64;
-    e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
-    e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
+    e.obs0 = static_cast<long>(8) * m->M * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
+    e.col_group = 64; e.col_group_stride = static_cast<long>(m->M) * 64;  // head h = column / 64 -> its own [M, 64] block
+    e.bias = m->ca_k_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 512;
     gemm(c, a, w, e);
   }
   {  // V_c[b][dl][h][m][64] = memory Wv^T + bv, same head-major layout: a 64-key block of one (image, layer, head) is
@@ -395,11 +396,12 @@ void omni_encode(Ctx* c, const float* img, const uint8_t* mask, int B, int H, in
     Operand a = act_op(mem.hi, mem.lo, m->M, 512, 512);
     a.nb1 = B; a.bs1 = static_cast<long>(m->M) * 512;
     Operand w = m->ca_v_all.w.op();
-    w.rows = 64; w.nb0 = 32 * c->kv_decoders; w.bs0 = static_cast<long>(64) * 512;
+    w.rows = 512; w.nb0 = 4 * c->kv_decoders; w.bs0 = static_cast<long>(512) * 512;
     Epilogue e;
     e.out_hi = m->vc_hi; e.out_lo = m->vc_lo; e.ldo = 64;
-    e.obs0 = static_cast<long>(m->M) * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
-    e.bias = m->ca_v_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 64;
+    e.obs0 = static_cast<long>(8) * m->M * 64; e.obs1 = static_cast<long>(96) * m->M * 64;
+    e.col_group = 64; e.col_group_stride = static_cast<long>(m->M) * 64;
+    e.bias = m->ca_v_all.b; e.bias_mode = BIAS_COL; e.bias_bs0 = 512;
     gemm(c, a, w, e);
   }
   if (m->vt_hi) {  // V_c^T[b, dl*512 + f, m] = Wv memory^T + bv  (feature-major so that P.V is a K-major GEMM)
