@@ -13,12 +13,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 // (x, y) -> packed bf16x2 hi and lo words with hi + lo == value to ~2^-17
+// (packed F2FP conversions: same round-to-nearest values as two scalar split_bf16, but off the XU pipe the exponentials use)
 __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 hx, lx, hy, ly;
-  split_bf16(x, hx, lx);
-  split_bf16(y, hy, ly);
-  hi = pack_bf16(hx, hy);
-  lo = pack_bf16(lx, ly);
+  split_pack2_bf16(x, y, hi, lo);
 }
 
 // four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3)

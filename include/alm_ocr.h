@@ -160,7 +160,12 @@ ALM_API int alm_stream_release(alm_ctx* ctx, void* consumer_stream /* cudaStream
  *           the converted bf16 hi/lo planes and fp32 vectors travel once over NVLink straight into place
  *   batch : alm_gather_sequences(ctx, buf, bytes, recv): all-gather of one fixed-size packed buffer per rank
  *           (send: host or device; recv: host, world * bytes, rank-major, or NULL), on the context's stream.
- * With world == 1 (no communicator) broadcast is a no-op and gather a copy. */
+ * With world == 1 (no communicator) broadcast is a no-op and gather a copy.
+ * Several contexts of one process (each with its own communicator) must issue their collectives in ONE order that is the
+ * same on every rank -- NCCL's rule for multiple communicators: a gather kernel spins on the device until its peers arrive,
+ * and two ranks that start different contexts' gathers first can block each other for good.  Number the batches the same
+ * way on every rank and issue gather(batch s) only after gather(batch s - 1) returned (dist.CollectiveOrder in the Python
+ * adapter; a mutex + counter in a C host). */
 ALM_API int alm_comm_unique_id(void* id128);
 ALM_API int alm_comm_init(alm_ctx* ctx, const void* id128, int rank, int world);
 ALM_API int alm_comm_attach(alm_ctx* ctx, void* nccl_comm /* ncclComm_t, caller-owned */, int rank, int world);
