@@ -221,7 +221,7 @@ struct Ctx {
   int fuse_ln_gemv = 1;  // point loop: 1 = the pre-LayerNorms run inside the following GEMV (13 fewer dependent launches per token)
   int kv_decoders = 3;  // number of decoders (pt, poly, rec order) whose cross-attention K/V caches alm_omni_encode fills
   int attn_impl = 0;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM
-  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel, 2 = tcgen05 + TMA (wattn_tc.cu)
+  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel, 2 = tcgen05 + TMA (wattn_tc.cu), 3 = persistent TMA-fed mma.sync over head pairs (wattn_ms.cu)
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
   struct GemmRec { cudaEvent_t a, b; double flops; };
@@ -281,6 +281,8 @@ void attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, long ld, int B
 
 // the same on tcgen05 with TMA-staged window tiles, two windows per M = 128 tile (wattn_tc.cu)
 void window_attention_tc(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B, int shift,
+                         int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
+void window_attention_ms(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int C, int heads, int nWh, int nWw, int B, int shift,
                          int Hp, int Wp, const float* bias_dense, bf16* out_hi, bf16* out_lo, float* out_f32);
 
 void split_rows(Ctx* c, const float* src, long lds, long rows, int C, bf16* hi, bf16* lo, long ldo);

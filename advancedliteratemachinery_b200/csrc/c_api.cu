@@ -195,7 +195,7 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
       ALM_REQUIRE(value == 0 || value == 1, ALM_ERR_INVALID, "attn_impl must be 0 or 1");
       h->c.attn_impl = static_cast<int>(value);
     } else if (k == "wattn_impl") {
-      ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "wattn_impl must be 0, 1 or 2");
+      ALM_REQUIRE(value >= 0 && value <= 3, ALM_ERR_INVALID, "wattn_impl must be 0 .. 3");
       h->c.wattn_impl = static_cast<int>(value);
     } else if (k == "enc_grid_cap") {
       h->c.enc_grid_cap = static_cast<int>(value);

@@ -644,6 +644,10 @@ void window_attention_split(Ctx* c, const bf16* qkv_hi, const bf16* qkv_lo, int 
     window_attention_tc(c, qkv_hi, qkv_lo, C, heads, nWh, nWw, B, shift, Hp, Wp, bias_dense, out_hi, out_lo, out_f32);
     return;
   }
+  if (c->wattn_impl == 3 && heads % 2 == 0) {  // persistent TMA-fed mma.sync kernel over head pairs (wattn_ms.cu)
+    window_attention_ms(c, qkv_hi, qkv_lo, C, heads, nWh, nWw, B, shift, Hp, Wp, bias_dense, out_hi, out_lo, out_f32);
+    return;
+  }
   dim3 grid(static_cast<unsigned>(B * nWh * nWw), heads);
   window_attention_split_kernel<<<grid, 128, 0, c->stream>>>(qkv_hi, qkv_lo, C, nWh, nWw, shift, Hp, Wp, bias_dense, out_hi,
                                                              out_lo, out_f32);

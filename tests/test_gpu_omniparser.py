@@ -103,7 +103,8 @@ def test_window_attention_core(ctx, B, nWh, nWw, heads, shift):
         attn = (attn.view(B, nWh * nWw, heads, 49, 49) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, 49, 49)
     ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(rows, C)
     qd, td = qkv.cuda(), tab.cuda()
-    for impl, tol in ((0, 5e-5), (1, 5e-6), (2, 5e-5)):  # mma.sync kernel, fp32 SIMT debug kernel, tcgen05 + TMA kernel
+    # mma.sync kernel, fp32 SIMT debug kernel, tcgen05 + TMA kernel, persistent TMA-fed mma.sync kernel over head pairs
+    for impl, tol in ((0, 5e-5), (1, 5e-6), (2, 5e-5), (3, 5e-5)):
         ctx.set_option('wattn_impl', impl)
         out = torch.full((rows, C), float('nan'), device='cuda')
         ctx.check(ctx.lib.alm_op_window_attention(ctx.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, C,
