@@ -222,16 +222,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         ptx::mbar_wait(s_full, s_phase);
         s_phase ^= 1;
         ptx::tc_fence_after();
-        // pass 1: maximum over this half's live keys
+        // pass 1: maximum over this half's live keys.  Only the chunk that contains key T needs per-key predicates; the
+        // chunks in front of it run a straight-line max tree (the predicated form was ~13 instructions per key)
         float m = -INFINITY;
         if (warp_live) {
           for (int c = c_lo; c < c_hi; ++c) {
             uint32_t v[16];
             ptx::tmem_ld_32x16(lane_addr + S_COL + c * 16, v);
             ptx::tmem_ld_wait();
+            if ((c + 1) * 16 <= p.T) {
+              float a0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), a1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+              for (int j = 4; j < 16; j += 4) {
+                a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+              }
+              m = fmaxf(m, fmaxf(a0, a1));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+            }
           }
         }
         xch[hf * 128 + r] = m;
@@ -241,21 +252,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         // pass 2: p = 2^((s - m) * c); partial row sum; bf16 (hi, lo) pairs back into tensor memory
         float l = 0.f;
         if (warp_live) {
-          const float mc = m * p.scale_log2e;
+          const float sl2 = p.scale_log2e;
+          const float mc = m * sl2;
+          float l0 = 0.f, l1 = 0.f;
           for (int c = c_lo; c < c_hi; ++c) {
             uint32_t v[16], ph[8], pl[8];
             ptx::tmem_ld_32x16(lane_addr + S_COL + c * 16, v);
             ptx::tmem_ld_wait();
+            if ((c + 1) * 16 <= p.T) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float e0 = c * 16 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mc)) : 0.f;
-              float e1 = c * 16 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mc)) : 0.f;
-              l += e0 + e1;
-              split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
+              for (int j = 0; j < 16; j += 2) {
+                const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mc));
+                const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mc));
+                l0 += e0;
+                l1 += e1;
+                split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float e0 = c * 16 + j < p.T ? ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mc)) : 0.f;
+                const float e1 = c * 16 + j + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mc)) : 0.f;
+                l0 += e0;
+                l1 += e1;
+                split_pack2_bf16(e0, e1, ph[j >> 1], pl[j >> 1]);
+              }
             }
             ptx::tmem_st_32x8(lane_addr + P_COL + c * 8, ph);
             if (NSPLIT == 3) ptx::tmem_st_32x8(lane_addr + plo_base + (c - c_lo) * 8, pl);  // behind this thread's read pointer
           }
+          l = l0 + l1;
           ptx::tmem_st_wait();
         }
         ptx::tc_fence_before();

@@ -31,6 +31,11 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ int lds_s32(uint32_t saddr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));

@@ -31,6 +31,7 @@ constexpr int WM_TILE = 64 * 128;            // one (plane, q|k|v) tile: 64 rows
 constexpr int WM_STAGE = 6 * WM_TILE;        // hi q,k,v then lo q,k,v
 constexpr int WM_BIASP = 56;                 // floats per staged bias row: 8 rows x 8 banks per half-warp, conflict-free float2
 constexpr int WM_OUTP = 36;                  // floats per row of a warp's 16 x 32 output staging block
+constexpr float WM_LOG2E = 1.4426950408889634f;
 
 struct WmSmem {
   static constexpr int kTiles = 0;
@@ -51,6 +52,12 @@ struct WmParams {
   bf16* out_lo;
   float* out_f32;
 };
+
+__device__ __forceinline__ float wm_ex2(float x) {   // 2^x, MUFU.EX2 (2 ulp); 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // byte offset of 16-byte chunk `chunk` of row `row` inside a 128-byte-swizzled tile (tile base 1024-byte aligned)
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
@@ -85,7 +92,8 @@ window_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   }
   for (int i = tid; i < 2 * WM_WT * WM_WT; i += WM_THREADS) {
     const int hh = i / (WM_WT * WM_WT), rem = i % (WM_WT * WM_WT);
-    sbias[(hh * WM_WT + rem / WM_WT) * WM_BIASP + rem % WM_WT] = p.bias[static_cast<long>(pair * 2 + hh) * WM_WT * WM_WT + rem];
+    sbias[(hh * WM_WT + rem / WM_WT) * WM_BIASP + rem % WM_WT] =
+        p.bias[static_cast<long>(pair * 2 + hh) * WM_WT * WM_WT + rem] * WM_LOG2E;   // base-2 softmax: exp(x) = 2^(x log2 e)
   }
   __syncthreads();
 
@@ -117,9 +125,10 @@ window_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   const int g = lane >> 2, t = lane & 3;
   const int lrow = lane & 7, lmat = lane >> 3;
   const int r_lo = band * 16 + g, r_hi = r_lo + 8;
-  const float* bias_h = sbias + hh * WM_WT * WM_BIASP;
+  const uint32_t bias_h = ptx::smem_u32(sbias + hh * WM_WT * WM_BIASP);   // explicit ld.shared below (generic LD otherwise)
   float* so = reinterpret_cast<float*>(smem + L::kOut) + warp * 16 * WM_OUTP;
   int* sreg = reinterpret_cast<int*>(smem + L::kReg) + warp * 64;
+  const uint32_t sreg_a = ptx::smem_u32(sreg);
   const uint32_t tiles = ptx::smem_u32(smem + L::kTiles);
   const int head = pair * 2 + hh;
 
@@ -170,21 +179,26 @@ window_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         mma_bf16_16816(sc[j], aq[0][ks], bl[2 * ks], bl[2 * ks + 1]);
       }
     }
-    // ---- + relative-position bias + shift mask; padding columns excluded; softmax per row (fp32)
-    const int reg_lo = p.shift > 0 ? sreg[r_lo] : 0, reg_hi = p.shift > 0 ? sreg[r_hi] : 0;
+    // ---- + relative-position bias + shift mask; padding columns excluded; softmax per row in base 2 (fp32): the scores
+    //      are carried as x log2(e) (bias pre-multiplied in shared memory), so each probability is one FADD + MUFU.EX2
+    const int reg_lo = p.shift > 0 ? ptx::lds_s32(sreg_a + r_lo * 4) : 0, reg_hi = p.shift > 0 ? ptx::lds_s32(sreg_a + r_hi * 4) : 0;
     float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int col = 8 * j + 2 * t;
       float2 b_lo = make_float2(0.f, 0.f), b_hi = make_float2(0.f, 0.f);
-      if (r_lo < WM_WT) b_lo = *reinterpret_cast<const float2*>(bias_h + r_lo * WM_BIASP + col);
-      if (r_hi < WM_WT) b_hi = *reinterpret_cast<const float2*>(bias_h + r_hi * WM_BIASP + col);
+      if (r_lo < WM_WT) b_lo = ptx::lds_f32x2(bias_h + (r_lo * WM_BIASP + col) * 4);
+      if (r_hi < WM_WT) b_hi = ptx::lds_f32x2(bias_h + (r_hi * WM_BIASP + col) * 4);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         if (col + e < WM_WT) {
-          const int rc = p.shift > 0 ? sreg[col + e] : 0;
-          sc[j][e] += (e ? b_lo.y : b_lo.x) + ((p.shift > 0 && rc != reg_lo) ? -100.0f : 0.0f);
-          sc[j][2 + e] += (e ? b_hi.y : b_hi.x) + ((p.shift > 0 && rc != reg_hi) ? -100.0f : 0.0f);
+          sc[j][e] = fmaf(sc[j][e], WM_LOG2E, e ? b_lo.y : b_lo.x);
+          sc[j][2 + e] = fmaf(sc[j][2 + e], WM_LOG2E, e ? b_hi.y : b_hi.x);
+          if (p.shift > 0) {
+            const int rc = ptx::lds_s32(sreg_a + (col + e) * 4);
+            if (rc != reg_lo) sc[j][e] += -100.0f * WM_LOG2E;
+            if (rc != reg_hi) sc[j][2 + e] += -100.0f * WM_LOG2E;
+          }
         } else {
           sc[j][e] = -INFINITY;
           sc[j][2 + e] = -INFINITY;
@@ -200,8 +214,8 @@ window_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     for (int j = 0; j < 7; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        sc[j][e] = expf(sc[j][e] - m_lo);
-        sc[j][2 + e] = expf(sc[j][2 + e] - m_hi);
+        sc[j][e] = wm_ex2(sc[j][e] - m_lo);
+        sc[j][2 + e] = wm_ex2(sc[j][2 + e] - m_hi);
         sum_lo += sc[j][e];
         sum_hi += sc[j][2 + e];
       }
