@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libalm_ocr.so')
+# ALM_OCR_LIB: developer knob for A/B runs of two builds of the same library on one GPU box (never a different backend)
+LIB_PATH = os.environ.get('ALM_OCR_LIB') or os.path.join(_HERE, 'libalm_ocr.so')
 
 ALM_OK = 0
 MODEL_OMNI_SPOT, MODEL_OMNI_KIE, MODEL_MGPSTR = 1, 2, 3
@@ -137,6 +138,11 @@ class Context:
         self.h = h
         self.device = device
         self.comm_rank, self.comm_world = 0, 1
+        # ALM_OCR_OPTIONS="name=value,...": developer knob, applied to every new context (A/B runs of kernel variants
+        # through the unchanged tests / bench; the options are the documented alm_set_option ones)
+        for kv in filter(None, os.environ.get('ALM_OCR_OPTIONS', '').split(',')):
+            k, v = kv.split('=')
+            self.set_option(k.strip(), int(v))
 
     def check(self, rc):
         if rc != ALM_OK:

@@ -221,7 +221,7 @@ struct Ctx {
   int fuse_ln_gemv = 1;  // point loop: 1 = the pre-LayerNorms run inside the following GEMV (13 fewer dependent launches per token)
   int kv_decoders = 3;  // number of decoders (pt, poly, rec order) whose cross-attention K/V caches alm_omni_encode fills
   int attn_impl = 0;   // ViT attention: 0 = fused tcgen05 kernel with S / P in tensor memory (attn_tc.cu), 1 = GEMM + softmax + GEMM
-  int wattn_impl = 0;  // 0 = mma.sync split-bf16 window attention, 1 = fp32 SIMT debug kernel, 2 = tcgen05 + TMA (wattn_tc.cu), 3 = persistent TMA-fed mma.sync over head pairs (wattn_ms.cu)
+  int wattn_impl = 3;  // 3 = persistent TMA-fed mma.sync kernel over head pairs (wattn_ms.cu; odd head counts fall back to 0), 0 = one CTA per (window, head), 1 = fp32 SIMT debug kernel, 2 = tcgen05 + TMA (wattn_tc.cu)
   // optional per-GEMM event timing (alm_set_option "profile_gemm" 1; read with alm_profile_read)
   int profile_gemm = 0;
   struct GemmRec { cudaEvent_t a, b; double flops; };

@@ -216,7 +216,8 @@ int alm_set_option(alm_ctx* h, const char* key, long value) {
     } else if (k == "small_grid_cap") {
       h->c.small_grid_cap = static_cast<int>(value);
     } else if (k == "gemm_plain_epilogue") {
-      h->c.gemm_plain_epilogue = value ? 1 : 0;
+      ALM_REQUIRE(value >= 0 && value <= 2, ALM_ERR_INVALID, "gemm_plain_epilogue must be 0, 1 or 2");
+      h->c.gemm_plain_epilogue = static_cast<int>(value);
     } else if (k == "wide_tiles") {
       h->c.wide_tiles = value ? 1 : 0;
     } else if (k == "decode_streams") {

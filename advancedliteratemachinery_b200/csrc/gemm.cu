@@ -163,6 +163,7 @@ template <int BLOCK_N, int NSPLIT, int PLAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                     const GemmParams p) {
   using L = SmemLayout<BLOCK_N, NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
@@ -297,6 +298,78 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (PLAIN == 2) {
+    // ===================================================================== epilogue warps (8), TMA-store form
+    // Launches whose only output is an unbatched split-bf16 matrix with column bias / activation (the qkv and fc1 GEMMs:
+    // 7/8 of a transformer block's output elements).  The accumulator block stays ROW-PER-THREAD as tcgen05.ld delivers it
+    // (thread = row, 32 consecutive columns): bias / GELU / the hi-lo split run on fp32 pairs in registers, the bf16 rows
+    // go to a 64-byte-swizzled staging block with conflict-free 16-byte stores, and ONE lane hands the 32 x 32 block to
+    // the TMA unit (cp.async.bulk.tensor store, one per plane), which clips the M tail.  No fp32 transpose through shared
+    // memory, no per-thread global addressing or store instructions: the epilogue was the bound of every small-K launch
+    // (ncu: ~30 thread-instructions per output element of a GELU + split epilogue).
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
+    const int half = (warp - 2) >> 2;      // 32-column chunks c = half, half + 2, ... of the tile
+    const uint32_t stg = ptx::smem_u32(smem + L::kBudget + L::kBarBytes) + (warp - 2) * 4096;  // hi block, lo block at +2048
+    const uint32_t row_off = lane * 64, sw = (lane >> 1) & 3;   // 64B swizzle: 16-byte chunk k of row r sits at k ^ ((r >> 1) & 3)
+    const Epilogue& e = p.e;
+    const f2 al = f2_splat(e.alpha);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int rem = static_cast<int>(tile % tiles_per_batch);
+      const int m_blk = rem / p.n_blocks, n_blk = rem % p.n_blocks;
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+      const int row_base = m_blk * BLOCK_M + quarter * 32;
+      const bool rows_live = row_base < p.M;
+#pragma unroll 1
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + c * 32, v);
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        const bool live = rows_live && col0 < p.N;   // warp-uniform; N % 32 == 0 for these launches
+        float4 bb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          bb[q] = (e.bias && live) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ptx::tmem_ld_wait();
+        if (!live) continue;
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          f2 a = f2_fma(f2_make(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), al, f2_make(bb[q].x, bb[q].y));
+          f2 b = f2_fma(f2_make(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), al, f2_make(bb[q].z, bb[q].w));
+          if (e.act == ACT_GELU) { a = gelu_erf2(a); b = gelu_erf2(b); }
+          float f0, f1, f2_, f3;
+          f2_get(a, f0, f1); f2_get(b, f2_, f3);
+          if (e.act == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2_ = fmaxf(f2_, 0.f); f3 = fmaxf(f3, 0.f); }
+          split_pack_bf16x2(f0, f1, ph[2 * q], pl[2 * q]);
+          split_pack_bf16x2(f2_, f3, ph[2 * q + 1], pl[2 * q + 1]);
+        }
+        // the previous block of this warp must have left the staging area before it is rewritten
+        if (lane == 0) ptx::tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t dst = stg + row_off + ((k ^ sw) << 4);
+          ptx::sts_v4(dst, ph[4 * k], ph[4 * k + 1], ph[4 * k + 2], ph[4 * k + 3]);
+          if (e.out_lo) ptx::sts_v4(dst + 2048, pl[4 * k], pl[4 * k + 1], pl[4 * k + 2], pl[4 * k + 3]);
+        }
+        ptx::fence_proxy_async();   // generic-proxy writes -> visible to the async proxy (TMA)
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tm_o_hi, stg, col0, row_base);
+          if (e.out_lo) ptx::tma_store_2d(&tm_o_lo, stg + 2048, col0, row_base);
+          ptx::tma_store_commit();
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) ptx::tma_store_wait_all();   // the staging blocks must outlive the last stores
   } else {
     // ===================================================================== epilogue warps (8)
     // warp -> (TMEM lane quarter, column half).  Each 32x32 accumulator block is read row-per-thread from TMEM,
@@ -531,6 +604,26 @@ const CUtensorMap& make_tmap(Ctx* c, const bf16* base, const Operand& op, int bo
   return c->tmap_cache.emplace(key, tm).first->second;
 }
 
+// 2-D map of one output plane for the TMA-store epilogue: [M rows, N columns] bf16 with leading dimension ldo, boxes of
+// 32 x 32 elements (64-byte rows, 64-byte swizzle).  Memoised like the operand maps (the decode loop repeats its launches).
+const CUtensorMap& make_out_tmap(Ctx* c, const bf16* base, int M, int N, long ldo) {
+  Ctx::TmapKey key{base, N, M, ldo, -2, 0, 0, 0, 32, 0};
+  auto it = c->tmap_cache.find(key);
+  if (it != c->tmap_cache.end()) return it->second;
+  if (c->tmap_cache.size() > 20000) c->tmap_cache.clear();
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {cuuint64_t(N), cuuint64_t(M)};
+  cuuint64_t strides[1] = {cuuint64_t(ldo) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw AlmError{ALM_ERR_CUDA, "cuTensorMapEncodeTiled (gemm output plane) failed with CUresult " + std::to_string(int(r))};
+  return c->tmap_cache.emplace(key, tm).first->second;
+}
+
 template <int BLOCK_N, int NSPLIT, int PLAIN>
 void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   using L = SmemLayout<BLOCK_N, NSPLIT>;
@@ -560,13 +653,16 @@ void launch_tc(Ctx* c, const Operand& A, const Operand& B, GemmParams& p) {
   const CUtensorMap ta_hi = make_tmap(c, A.hi, A, a_rows, pa);
   const CUtensorMap tb_hi = make_tmap(c, B.hi, B, BLOCK_N, pb);
   const CUtensorMap ta_lo = ta_hi, tb_lo = tb_hi;  // kept in the signature; the 5-D maps cover both planes
+  // TMA-store epilogue: 2-D maps of the output planes (32 x 32 bf16 boxes, 64-byte swizzle); placeholders otherwise
+  const CUtensorMap to_hi = PLAIN == 2 ? make_out_tmap(c, p.e.out_hi, p.M, p.N, p.e.ldo) : ta_hi;
+  const CUtensorMap to_lo = (PLAIN == 2 && p.e.out_lo) ? make_out_tmap(c, p.e.out_lo, p.M, p.N, p.e.ldo) : to_hi;
   // Small launches (the per-token decode GEMMs) leave half of the SMs to the kernels of the other in-flight
   // streams / batches: every CTA of this kernel needs a whole SM (231 KB of shared memory).
   long cap = c->num_sms;
   if (c->gemm_grid_cap > 0) cap = std::min<long>(cap, c->gemm_grid_cap);
   if (c->small_grid_cap > 0 && p.num_tiles <= 2L * c->num_sms) cap = c->small_grid_cap;
   const int grid = static_cast<int>(std::min<long>(p.num_tiles, cap));
-  kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  kern<<<grid, kThreads, L::kTotal, c->stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p);
 }
 
 }  // namespace
@@ -626,20 +722,29 @@ void gemm(Ctx* c, const Operand& A, const Operand& B, const Epilogue& E) {
                       static_cast<long>(p.m_blocks) * ((p.N + 255) / 256) * p.nb0 * p.nb1 >= 2L * c->num_sms;
     // map-free, vector-aligned launches take the slim epilogue
     const bool plain = c->gemm_plain_epilogue && !E.out_map && !E.resid_map && E.bias_mode != BIAS_ROW && vec && p.N % 4 == 0;
+    // ... and, when the only output is an unbatched split-bf16 matrix (qkv / fc1), the TMA-store form of it
+    const bool tma_out = plain && c->gemm_plain_epilogue >= 2 && !narrow && !E.resid && !E.out_f32 && E.out_hi &&
+                         p.nb0 * p.nb1 == 1 && p.N % 32 == 0 && E.col_group == 0;
 #define ALM_LAUNCH(BNV, NSV)                                  \
   do {                                                        \
     if (plain) launch_tc<BNV, NSV, 1>(c, A, B, p);            \
     else launch_tc<BNV, NSV, 0>(c, A, B, p);                  \
   } while (0)
+#define ALM_LAUNCH_T(BNV, NSV)                                \
+  do {                                                        \
+    if (tma_out) launch_tc<BNV, NSV, 2>(c, A, B, p);          \
+    else ALM_LAUNCH(BNV, NSV);                                \
+  } while (0)
     if (nsplit == 3) {
       if (narrow) ALM_LAUNCH(32, 3);
-      else if (wide) ALM_LAUNCH(256, 3);
-      else ALM_LAUNCH(128, 3);
+      else if (wide) ALM_LAUNCH_T(256, 3);
+      else ALM_LAUNCH_T(128, 3);
     } else {
       if (narrow) ALM_LAUNCH(32, 1);
-      else if (wide) ALM_LAUNCH(256, 1);
-      else ALM_LAUNCH(128, 1);
+      else if (wide) ALM_LAUNCH_T(256, 1);
+      else ALM_LAUNCH_T(128, 1);
     }
+#undef ALM_LAUNCH_T
 #undef ALM_LAUNCH
   }
   if (c->profile_gemm) {

@@ -20,6 +20,17 @@
 namespace alm {
 namespace {
 
+// The softmax runs in base 2: scores are scaled by head_dim^-0.5 * log2(e) in the one multiply that applied the 1/8
+// before, running maxima / partial maxima are kept in those units, and every exponential is one MUFU.EX2 (2 ulp) --
+// expf cost ~8 instructions per score on a kernel whose issue slots compete with the HMMA stream.
+constexpr float XA_SCALE_LOG2E = 0.125f * 1.4426950408889634f;
+__device__ __forceinline__ float xa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+
 constexpr int TX_KB = 64;            // keys per block
 constexpr int TX_PLANE = 64 * 128;   // bytes of one plane tile: 64 keys x 64 bf16
 constexpr int TX_STAGE = 4 * TX_PLANE;
@@ -205,8 +216,8 @@ cross_attn_tma_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_co
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool dead = (mbits >> (2 * j + e)) & 1u;
-        s[j][e] = dead ? -INFINITY : s[j][e] * 0.125f;
-        s[j][2 + e] = dead ? -INFINITY : s[j][2 + e] * 0.125f;
+        s[j][e] = dead ? -INFINITY : s[j][e] * XA_SCALE_LOG2E;
+        s[j][2 + e] = dead ? -INFINITY : s[j][2 + e] * XA_SCALE_LOG2E;
         mx_lo = fmaxf(mx_lo, s[j][e]);
         mx_hi = fmaxf(mx_hi, s[j][2 + e]);
       }
@@ -215,7 +226,7 @@ cross_attn_tma_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_co
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
     const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
     const float mu_lo = (mn_lo == -INFINITY) ? 0.f : mn_lo, mu_hi = (mn_hi == -INFINITY) ? 0.f : mn_hi;
-    const float sc_lo = expf(m_lo - mu_lo), sc_hi = expf(m_hi - mu_hi);  // exp(-inf) == 0 on the first live block
+    const float sc_lo = xa_ex2(m_lo - mu_lo), sc_hi = xa_ex2(m_hi - mu_hi);  // 2^-inf == 0 on the first live block
     m_lo = mn_lo; m_hi = mn_hi;
     l_lo *= sc_lo; l_hi *= sc_hi;
 #pragma unroll
@@ -227,8 +238,8 @@ cross_attn_tma_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_co
     for (int j = 0; j < NJ; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        s[j][e] = expf(s[j][e] - mu_lo);
-        s[j][2 + e] = expf(s[j][2 + e] - mu_hi);
+        s[j][e] = xa_ex2(s[j][e] - mu_lo);
+        s[j][2 + e] = xa_ex2(s[j][2 + e] - mu_hi);
         l_lo += s[j][e];
         l_hi += s[j][2 + e];
       }
@@ -309,7 +320,7 @@ cross_attn_tma_kernel(const __grid_constant__ CUtensorMap tm_kh, const __grid_co
       for (int sidx = 0; sidx < nparts; ++sidx) {
         const float* ps = base + sidx * sstride;
         const float ms = ps[0];
-        const float w = (ms == -INFINITY) ? 0.f : expf(ms - mm);
+        const float w = (ms == -INFINITY) ? 0.f : xa_ex2(ms - mm);   // partial maxima are in log2 units
         ltot += w * ps[1];
 #pragma unroll
         for (int i = 0; i < DPT; i += 2) {

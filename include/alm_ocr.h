@@ -86,9 +86,9 @@ ALM_API const char* alm_version(void);
  *          [default]; 1 = only the point decoder's, for callers that run alm_omni_decode_points alone),
  *          "attn_impl" (ViT attention of MGP-STR: 0 = fused tcgen05 kernel, scores / probabilities in tensor memory
  *          [default]; 1 = score GEMM + softmax + P.V GEMM, the A/B reference),
- *          "wattn_impl" (0 = mma.sync window attention [default], 1 = fp32 SIMT debug kernel, 2 = tcgen05 kernel with
+ *          "wattn_impl" (0 = mma.sync window attention, one CTA per (window, head), 1 = fp32 SIMT debug kernel, 2 = tcgen05 kernel with
  *          TMA-staged window tiles, two windows per M = 128 tile, scores / probabilities in tensor memory, 3 = persistent
- *          mma.sync kernel fed by a TMA + mbarrier ring, one head pair per 128-byte row segment, bias in shared memory),
+ *          mma.sync kernel fed by a TMA + mbarrier ring, one head pair per 128-byte row segment, bias in shared memory [default]),
  *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
  *          streams / in-flight batches can share the GPU),
  *          "gemm_plain_epilogue" (1 = map-free GEMM launches use the slim epilogue specialisation [default], 0 = generic),

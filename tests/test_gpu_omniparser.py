@@ -110,7 +110,7 @@ def test_window_attention_core(ctx, B, nWh, nWw, heads, shift):
         ctx.check(ctx.lib.alm_op_window_attention(ctx.h, qd.data_ptr(), td.data_ptr(), out.data_ptr(), B, nWh, nWw, C,
                                                   heads, shift))
         assert float((out.cpu() - ref).abs().max()) < tol, impl
-    ctx.set_option('wattn_impl', 0)
+    ctx.set_option('wattn_impl', 3)   # back to the default
 
 
 # ----------------------------------------------------------------------------------------------- model
