@@ -5,7 +5,7 @@
 //     O = P V            tcgen05.mma with the A operand in TMEM and V as an MN-major shared-memory operand
 //
 // Neither the scores nor the probabilities ever exist in HBM (the unfused path wrote ~5 GB of them per layer at B = 512).
-// Reference arithmetic: timm-0.4.12 Attention (restated in oracle/shim/timm/models/vision_transformer.py; called from
+// Reference arithmetic: timm-0.4.12 Attention (timm/models/vision_transformer.py, class Attention; called from
 // OCR/MGP-STR/modules/mgp_str.py:73-74): attn = (q @ k^T) * head_dim^-0.5; softmax; attn @ v.
 //
 // One persistent CTA per SM walks the (crop, head) items.  Per item the keys / values of the head (all T <= 272 of them)
