@@ -205,7 +205,7 @@ struct Ctx {
   cudaEvent_t ev_order = nullptr;  // alm_stream_wait / alm_stream_release
   cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync event: host waits that sleep instead of spinning
   int small_grid_cap = 0;  // > 0: GEMM launches with <= 2*SMs tiles use at most this many CTAs
-  int gemm_plain_epilogue = 1;  // 1 = map-free launches use the slim epilogue specialisation (A/B: 0)
+  int gemm_plain_epilogue = 2;  // 2 = slim epilogue for map-free launches + TMA-store form for split-bf16-only outputs (qkv / fc1), 1 = slim only, 0 = generic (A/B)
   int wide_tiles = 1;      // 1 = 128x256 GEMM tiles for large problems
   int decode_streams = 2;  // 2 = poly and rec decode loops overlap on two streams, 1 = serial
   int use_graphs = 1;  // replay captured CUDA graphs for the per-token decode steps

@@ -91,7 +91,8 @@ ALM_API const char* alm_version(void);
  *          mma.sync kernel fed by a TMA + mbarrier ring, one head pair per 128-byte row segment, bias in shared memory [default]),
  *          "small_grid_cap" (0 = off [default]; n = small GEMM launches use at most n CTAs so that concurrent
  *          streams / in-flight batches can share the GPU),
- *          "gemm_plain_epilogue" (1 = map-free GEMM launches use the slim epilogue specialisation [default], 0 = generic),
+ *          "gemm_plain_epilogue" (2 = map-free GEMM launches use the slim epilogue specialisation and, when the only output is
+ *          an unbatched split-bf16 matrix, its TMA-store form [default]; 1 = slim only; 0 = generic),
  *          "wide_tiles" (1 = 128x256 GEMM tiles for large problems [default], 0 = 128x128 only),
  *          "decode_streams" (2 = polygon and recognition loops overlap on two streams [default], 1 = serial),
  *          "use_graphs" (1 = replay captured CUDA graphs for the per-token decode steps [default], 0 = eager),
