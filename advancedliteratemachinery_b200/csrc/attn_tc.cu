@@ -151,10 +151,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     int qs = 0;
     const uint32_t k_base = ptx::smem_u32(smem + L::kK), v_base = ptx::smem_u32(smem + L::kV);
     for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      ptx::mbar_wait(kv_full, kv_phase);
+      ptx::mbar_wait_hot(kv_full, kv_phase);
       kv_phase ^= 1;
       for (int i = 0; i < p.tiles; ++i) {
-        ptx::mbar_wait(&q_full[qs], q_phase);
+        ptx::mbar_wait_hot(&q_full[qs], q_phase);
         ptx::tc_fence_after();
         const uint32_t q_base = ptx::smem_u32(smem + L::kQ + qs * NP * AT_BOXB);
         if (ptx::elect_one()) {
@@ -178,9 +178,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         __syncwarp();
         if (++qs == AT_QSTAGES) { qs = 0; q_phase ^= 1; }
         // ---- O = P V once the softmax warps have written P (and the previous O has been drained)
-        ptx::mbar_wait(p_full, p_phase);
+        ptx::mbar_wait_hot(p_full, p_phase);
         p_phase ^= 1;
-        ptx::mbar_wait(o_empty, oe_phase ^ 1);
+        ptx::mbar_wait_hot(o_empty, oe_phase ^ 1);
         oe_phase ^= 1;
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -219,7 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const int r = quarter * 32 + lane;
         const int row = i * 128 + r;
         const bool warp_live = i * 128 + quarter * 32 < p.T;
-        ptx::mbar_wait(s_full, s_phase);
+        ptx::mbar_wait_hot(s_full, s_phase);
         s_phase ^= 1;
         ptx::tc_fence_after();
         // pass 1: maximum over this half's live keys.  Only the chunk that contains key T needs per-key predicates; the
@@ -294,7 +294,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         asm volatile("bar.sync 2, 256;" ::: "memory");
         // ---- epilogue: O / l -> split bf16 planes (operand of the projection GEMM), token-major [B*T, D]; this half
         //      writes output dims [32 hf, 32 hf + 32)
-        ptx::mbar_wait(o_full, o_phase);
+        ptx::mbar_wait_hot(o_full, o_phase);
         o_phase ^= 1;
         ptx::tc_fence_after();
         if (warp_live) {

@@ -151,7 +151,7 @@ window_attention_ms_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       }
       __syncwarp();
     }
-    ptx::mbar_wait(&full[s], ph);
+    ptx::mbar_wait_hot(&full[s], ph);
     const uint32_t st = tiles + s * WM_STAGE;
     const uint32_t q_hi = st, k_hi = st + WM_TILE, v_hi = st + 2 * WM_TILE;
     const uint32_t q_lo = st + 3 * WM_TILE, k_lo = st + 4 * WM_TILE, v_lo = st + 5 * WM_TILE;
