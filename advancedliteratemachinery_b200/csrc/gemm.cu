@@ -322,45 +322,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       ptx::tc_fence_after();
       const int row_base = m_blk * BLOCK_M + quarter * 32;
       const bool rows_live = row_base < p.M;
-#pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + c * 32, v);
-        const int col0 = n_blk * BLOCK_N + c * 32;
+      // The warp's BLOCK_N / 64 chunks are software-pipelined: the tcgen05.ld of chunk i + 1 is in flight while chunk i is
+      // computed (with two epilogue warps per scheduler the TMEM read latency was exposed once per chunk).
+      constexpr int NCH = BLOCK_N / 64;
+      const uint32_t t_acc = tmem_base + (uint32_t(quarter * 32) << 16) + as * BLOCK_N + half * 32;
+      uint32_t v[2][32];
+      ptx::tmem_ld_32x32(t_acc, v[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int col0 = n_blk * BLOCK_N + (half + 2 * ci) * 32;
         const bool live = rows_live && col0 < p.N;   // warp-uniform; N % 32 == 0 for these launches
         float4 bb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           bb[q] = (e.bias && live) ? __ldg(reinterpret_cast<const float4*>(e.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         ptx::tmem_ld_wait();
-        if (!live) continue;
-        uint32_t ph[16], pl[16];
+        if (ci + 1 < NCH) ptx::tmem_ld_32x32(t_acc + (ci + 1) * 64, v[(ci + 1) & 1]);
+        if (live) {
+          const uint32_t (&vc)[32] = v[ci & 1];
+          uint32_t ph[16], pl[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          f2 a = f2_fma(f2_make(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), al, f2_make(bb[q].x, bb[q].y));
-          f2 b = f2_fma(f2_make(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), al, f2_make(bb[q].z, bb[q].w));
-          if (e.act == ACT_GELU) { a = gelu_erf2(a); b = gelu_erf2(b); }
-          float f0, f1, f2_, f3;
-          f2_get(a, f0, f1); f2_get(b, f2_, f3);
-          if (e.act == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2_ = fmaxf(f2_, 0.f); f3 = fmaxf(f3, 0.f); }
-          split_pack_bf16x2(f0, f1, ph[2 * q], pl[2 * q]);
-          split_pack_bf16x2(f2_, f3, ph[2 * q + 1], pl[2 * q + 1]);
-        }
-        // the previous block of this warp must have left the staging area before it is rewritten
-        if (lane == 0) ptx::tma_store_wait_read();
-        __syncwarp();
+          for (int q = 0; q < 8; ++q) {
+            f2 a = f2_fma(f2_make(__uint_as_float(vc[4 * q]), __uint_as_float(vc[4 * q + 1])), al, f2_make(bb[q].x, bb[q].y));
+            f2 b = f2_fma(f2_make(__uint_as_float(vc[4 * q + 2]), __uint_as_float(vc[4 * q + 3])), al, f2_make(bb[q].z, bb[q].w));
+            if (e.act == ACT_GELU) { a = gelu_erf2(a); b = gelu_erf2(b); }
+            float f0, f1, f2_, f3;
+            f2_get(a, f0, f1); f2_get(b, f2_, f3);
+            if (e.act == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2_ = fmaxf(f2_, 0.f); f3 = fmaxf(f3, 0.f); }
+            split_pack_bf16x2(f0, f1, ph[2 * q], pl[2 * q]);
+            split_pack_bf16x2(f2_, f3, ph[2 * q + 1], pl[2 * q + 1]);
+          }
+          // the previous block of this warp must have left the staging area before it is rewritten
+          if (lane == 0) ptx::tma_store_wait_read();
+          __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t dst = stg + row_off + ((k ^ sw) << 4);
-          ptx::sts_v4(dst, ph[4 * k], ph[4 * k + 1], ph[4 * k + 2], ph[4 * k + 3]);
-          if (e.out_lo) ptx::sts_v4(dst + 2048, pl[4 * k], pl[4 * k + 1], pl[4 * k + 2], pl[4 * k + 3]);
-        }
-        ptx::fence_proxy_async();   // generic-proxy writes -> visible to the async proxy (TMA)
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&tm_o_hi, stg, col0, row_base);
-          if (e.out_lo) ptx::tma_store_2d(&tm_o_lo, stg + 2048, col0, row_base);
-          ptx::tma_store_commit();
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t dst = stg + row_off + ((k ^ sw) << 4);
+            ptx::sts_v4(dst, ph[4 * k], ph[4 * k + 1], ph[4 * k + 2], ph[4 * k + 3]);
+            if (e.out_lo) ptx::sts_v4(dst + 2048, pl[4 * k], pl[4 * k + 1], pl[4 * k + 2], pl[4 * k + 3]);
+          }
+          ptx::fence_proxy_async();   // generic-proxy writes -> visible to the async proxy (TMA)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tm_o_hi, stg, col0, row_base);
+            if (e.out_lo) ptx::tma_store_2d(&tm_o_lo, stg + 2048, col0, row_base);
+            ptx::tma_store_commit();
+          }
         }
       }
       // release the accumulator stage back to the MMA warp
