@@ -43,7 +43,7 @@ MGP_GFLOP_PER_CROP = 49.75
 
 WORKLOADS = {
     'omni': dict(kind='omni', page=1024, batch=16, n_inst=N_INST, pt_len=2 * N_INST, points_only=False, inflight=5,
-                 workspace_mb=20480, gemm=(65536, 2048, 512), gemm_name='Swin stage-2 fc1',
+                 workspace_mb=20480, gemm=(65536, 2048, 512), gemm_name='Swin stage-2 fc1', gemm_ncu='r02f_prof_gemm_fc1_metrics.csv',
                  text=f'OmniParser Swin-B text spotting, 1024x1024 synthetic pages, batch 16 per GPU, N={N_INST} '
                       f'instances/page pinned (pt 128 + poly 32 + rec {REC_LEN} tokens)'),
     'platypus': dict(kind='omni', page=896, batch=8, n_inst=N_INST, pt_len=2 * N_INST, points_only=False, inflight=5,
@@ -54,7 +54,7 @@ WORKLOADS = {
                   workspace_mb=40960, gemm=(115200, 2048, 512), gemm_name='Swin stage-2 fc1',
                   text='OmniParser 1920x1920 synthetic pages, batch 8 per GPU, one 512-token point-decoder sequence per page '
                        '(table head not released, SURVEY F4: generic pt decoder)'),
-    'mgpstr': dict(kind='mgp', batch=512, inflight=2, gemm=(131584, 3072, 768), gemm_name='ViT fc1',
+    'mgpstr': dict(kind='mgp', batch=512, inflight=2, gemm=(131584, 3072, 768), gemm_name='ViT fc1', gemm_ncu='r02f_prof_gemm_vit_fc1_metrics.csv',
                    text='MGP-STR ViT-Base, 512 synthetic 32x128 crops per GPU per step, ids + probabilities of the three heads'),
 }
 
@@ -586,7 +586,7 @@ def main():
                      'launch': f'{w["gemm_name"]} (bias + GELU + split-bf16 output), timed alone with CUDA events',
                      'shape': {'M': M_, 'N': N_, 'K': K_}, 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
                      'frac': achieved / burst,
-                     'traffic': ncu_traffic_bytes('r01_prof_gemm_fc1_metrics.csv') if name == 'omni' else None,
+                     'traffic': ncu_traffic_bytes(w.get('gemm_ncu', '')),
                      'algorithmic_bytes': float(M_ * K_ * 4 + N_ * K_ * 4 + M_ * N_ * 4) if nsplit == 3 else float(M_ * K_ * 2 + N_ * K_ * 2 + M_ * N_ * 4),
                      'peak_source': f'{peak_src}, bf16 burst (kernel timed alone)',
                      'mma_passes_per_flop': nsplit, 'tensor_pipe_frac': achieved * nsplit / burst,
