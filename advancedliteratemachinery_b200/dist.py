@@ -75,6 +75,88 @@ class CollectiveOrder:
         return out
 
 
+class CollectiveLane:
+    """The other way to keep one global order: ONE host thread per rank issues every collective of the job, in ticket
+    order, on ONE dedicated context / communicator.  The compute threads only `submit(ticket, fn)` and go on with their next
+    batch, so a rank that is momentarily ahead does not park its GPU work behind a peer's gather (with the synchronous form
+    every batch is a rendezvous of all ranks, and the job runs at the pace of the slowest rank PER BATCH instead of on
+    average).  `max_ahead` bounds how far the compute threads may run ahead of the lane."""
+
+    def __init__(self, max_ahead: int = 16, timeout_s: float = 300.0, keep: int = 64):
+        self._cv = threading.Condition()
+        self._items, self._results = {}, {}
+        self._next, self._stop = 0, True
+        self._failed: Optional[BaseException] = None
+        self._max_ahead, self._timeout, self._keep = max_ahead, timeout_s, keep
+        self._thread: Optional[threading.Thread] = None
+
+    def start(self, first_ticket: int = 0) -> None:
+        self.stop()
+        with self._cv:
+            self._items.clear()
+            self._results.clear()
+            self._next, self._stop, self._failed = first_ticket, False, None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self) -> None:
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+
+    def fail(self, exc: BaseException) -> None:
+        with self._cv:
+            if self._failed is None:
+                self._failed = exc
+            self._cv.notify_all()
+
+    def submit(self, ticket: int, fn: Callable) -> None:
+        with self._cv:
+            ok = self._cv.wait_for(lambda: self._failed is not None or ticket - self._next < self._max_ahead,
+                                   timeout=self._timeout)
+            if self._failed is not None:
+                raise RuntimeError(f'collective {ticket} not submitted: the lane failed') from self._failed
+            if not ok:
+                raise TimeoutError(f'collective {ticket}: the lane is stuck at ticket {self._next}')
+            self._items[ticket] = fn
+            self._cv.notify_all()
+
+    def _run(self) -> None:
+        while True:
+            with self._cv:
+                self._cv.wait_for(lambda: self._stop or self._failed is not None or self._next in self._items)
+                if self._stop or self._failed is not None:
+                    return
+                ticket = self._next
+                fn = self._items.pop(ticket)
+            try:
+                res = fn()
+            except BaseException as e:   # noqa: BLE001 -- handed to the waiting threads
+                self.fail(e)
+                return
+            with self._cv:
+                self._results[ticket] = res
+                self._results.pop(ticket - self._keep, None)
+                self._next = ticket + 1
+                self._cv.notify_all()
+
+    def drain(self, upto: int) -> None:
+        """Block until every ticket < `upto` has run."""
+        with self._cv:
+            ok = self._cv.wait_for(lambda: self._failed is not None or self._next >= upto, timeout=self._timeout)
+            if self._failed is not None:
+                raise RuntimeError('a collective failed') from self._failed
+            if not ok:
+                raise TimeoutError(f'collectives stuck at ticket {self._next} (waiting for {upto})')
+
+    def result(self, ticket: int):
+        with self._cv:
+            return self._results.get(ticket)
+
+
 # ------------------------------------------------------------------------------------------------ weights
 def init_comm(ctx, device: Optional[torch.device] = None):
     """Create the library's NCCL communicator for `ctx`: rank 0 makes the id, torch.distributed ships its 128 bytes."""

@@ -14,9 +14,10 @@ Workloads (BASELINE.json `configs`; the default is the one the headline metric i
             (32 over 4 GPUs), throughput only, NO parity oracle
 
 A step = one batch through the whole path.  `value`: inputs resident in HBM; `e2e`: the same metric through the adapter
-with pinned HOST inputs, H2D and D2H inside the timed region.  With N > 1 GPUs every step ends with ONE all-gather of the
-decoded sequences (alm_gather_sequences, the library's own NCCL communicator) inside the timed region, and the weights
-reach the ranks by ONE NCCL broadcast of the converted planes (alm_broadcast_weights).
+with pinned HOST inputs, H2D and D2H inside the timed region.  With N > 1 GPUs every step has ONE all-gather of the
+decoded sequences (alm_gather_sequences, the library's own NCCL communicator on a dedicated context; one host thread per
+rank issues the gathers in batch order -- dist.CollectiveLane -- and the timed region ends when the last one has completed),
+and the weights reach the ranks by ONE NCCL broadcast of the converted planes (alm_broadcast_weights).
 
 `--impl reference` times the reference algorithm (the CPU oracle port: fp32, no KV cache, memory repeated per instance,
 transformer.py:74-100) on the host cores on the SAME workload: one page (omni / table / platypus) or 32 crops (mgpstr)
@@ -318,6 +319,10 @@ def main():
                     'their launch gaps.  0 = the workload default')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
     ap.add_argument('--ref-budget-s', type=float, default=330.0, help='reference arm: stop adding timed steps past this')
+    ap.add_argument('--collectives', default='lane', choices=['lane', 'order'], help='N > 1: who issues the per-batch gathers. '
+                    'lane = one host thread per rank on a dedicated context / communicator, the compute threads do not wait '
+                    '(dist.CollectiveLane); order = every compute thread gathers on its own context\'s communicator, taking '
+                    'turns in batch order (dist.CollectiveOrder; the A/B reference)')
     ap.add_argument('--watchdog-s', type=float, default=600.0, help='a timed phase that takes longer dumps every host '
                     'thread\'s stack to stderr and exits non-zero (a hung collective must not burn the GPU box)')
     ap.add_argument('--cpu-child', nargs=3, default=None, help=argparse.SUPPRESS)
@@ -332,7 +337,7 @@ def main():
     import torch
     import torch.distributed as dist
     from advancedliteratemachinery_b200 import MGPSTRB200, NestedTensor, OmniParserB200, OmniVocab, _lib
-    from advancedliteratemachinery_b200.dist import CollectiveOrder, gather_sequences, init_comm, load_weights_broadcast
+    from advancedliteratemachinery_b200.dist import CollectiveLane, CollectiveOrder, gather_sequences, init_comm, load_weights_broadcast
     from advancedliteratemachinery_b200 import synthetic as W  # synthetic checkpoint (data only)
 
     torch.set_grad_enabled(False)
@@ -369,9 +374,18 @@ def main():
     if rank == 0:
         sd = W.mgpstr_state_dict(seed=0) if is_mgp else W.omniparser_state_dict(seed=0, pt_eos_bias=-30.0)
     t_w = time.time()
+    gctx, gstream = None, None
     if world > 1:
-        for cx in ctxs:                      # one communicator per context, created in the same order on every rank
-            init_comm(cx, device=dev)
+        # two communicators per rank: context 0's for the weight broadcast, and one on a dedicated context + stream for the
+        # per-batch gathers, which ONE host thread (the collective lane) issues in batch order
+        if args.collectives == 'lane':
+            init_comm(ctxs[0], device=dev)
+            gstream = torch.cuda.Stream()
+            gctx = _lib.Context(local, gstream.cuda_stream)
+            init_comm(gctx, device=dev)
+        else:
+            for cx in ctxs:                  # one communicator per context, created in the same order on every rank
+                init_comm(cx, device=dev)
         load_weights_broadcast(ctxs[0], kind, sd, src=0, device=dev)
     else:
         ctxs[0].load_state_dict(kind, sd)
@@ -408,51 +422,63 @@ def main():
         models[j].encode(x, None)
         return models[j].decode_points() if w['points_only'] else models[j].decode()
 
-    order = CollectiveOrder()
+    lane = CollectiveLane(max_ahead=2 * C_) if world > 1 and args.collectives == 'lane' else None
+    order = CollectiveOrder() if world > 1 and args.collectives == 'order' else None
+    turn_results = {}
 
-    def gather(j, out, s):
-        """ONE all-gather of the decoded sequences of step `s` over the context's NCCL communicator, issued in step order
-        (the same on every rank: several communicators may only be used in one global order, dist.CollectiveOrder)."""
-        if world == 1:
-            return None
-        return order.run(s, lambda: gather_now(j, out))
-
-    def gather_now(j, out):
+    def gather_now(out, gc):
+        """ONE all-gather of the decoded sequences of a batch over context `gc`'s NCCL communicator."""
         if is_mgp:
             ids, prob = out
             buf = np.concatenate([ids.numpy().reshape(-1), prob.numpy().view(np.int32).reshape(-1)])
-            return ctxs[j].gather(buf, world)
+            return gc.gather(buf, world)
         if w['points_only']:
             buf = np.zeros((B, 1 + 2 * w['pt_len']), dtype=np.int32)
             for b, (tok, pr) in enumerate(out):
                 buf[b, 0] = tok.numel()
                 buf[b, 1:1 + tok.numel()] = tok.numpy()
                 buf[b, 1 + w['pt_len']:1 + w['pt_len'] + tok.numel()] = pr.numpy().view(np.int32)
-            return ctxs[j].gather(buf, world)
-        return gather_sequences(out, vocab, n_pages=world * B, ctx=ctxs[j])
+            return gc.gather(buf, world)
+        return gather_sequences(out, vocab, n_pages=world * B, ctx=gc)
+
+    def gather(j, out, s):
+        if lane is not None:      # issued by the lane thread in batch order on the gather context; not waited for here
+            lane.submit(s, lambda: gather_now(out, gctx))
+        elif order is not None:   # this thread gathers on its own context, when it is batch s's turn
+            turn_results[s] = order.run(s, lambda: gather_now(out, ctxs[j]))
 
     def step_resident(j, s):
         out = run_model(j, dev_in)
-        return out, gather(j, out, s)
+        gather(j, out, s)
+        return out
 
     def step_e2e(j, s):
         out = run_model(j, host_in)
-        return out, gather(j, out, s)
+        gather(j, out, s)
+        return out
 
     def run_steps(fn, steps):
-        """`steps` batches; step s runs on context s % C (static, so that the per-context collectives line up across
-        ranks).  One host thread per context: the C calls release the GIL, the per-context streams overlap on the device."""
-        last = [None] * C_
+        """`steps` batches; step s runs on context s % C.  One host thread per context (the C calls release the GIL, the
+        per-context streams overlap on the device) + the collective lane.  Returns, per context, (last result, its gathered
+        copy) once every gather of the run has completed."""
+        outs = [None] * C_
         errors = []
-        order.reset(0)
+        turn_results.clear()
+        if lane is not None:
+            lane.start(0)
+        if order is not None:
+            order.reset(0)
 
         def worker(j):
             try:
                 for s in range(j, steps, C_):
-                    last[j] = fn(j, s)
-            except BaseException as e:       # release the other contexts' threads instead of leaving them in a collective
+                    outs[j] = fn(j, s)
+            except BaseException as e:       # do not leave the other threads waiting on the lane
                 errors.append(e)
-                order.fail(e)
+                if lane is not None:
+                    lane.fail(e)
+                if order is not None:
+                    order.fail(e)
         if C_ == 1:
             worker(0)
         else:
@@ -463,7 +489,11 @@ def main():
                 t.join()
         if errors:
             raise errors[0]
-        return last
+        if lane is not None:
+            lane.drain(steps)
+        last_step = [j + C_ * ((steps - 1 - j) // C_) if j < steps else None for j in range(C_)]
+        gathered = (lambda t: lane.result(t)) if lane is not None else (lambda t: turn_results.get(t))
+        return [(outs[j], gathered(last_step[j]) if last_step[j] is not None else None) for j in range(C_)]
 
     def timed(fn, steps, warmup):
         faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
@@ -473,9 +503,14 @@ def main():
             faulthandler.cancel_dump_traceback_later()
 
     def timed_(fn, steps, warmup):
-        order.reset(0)
-        for j in range(C_):          # every context runs once (graph capture, descriptor caches) ...
+        if lane is not None:
+            lane.start(0)
+        if order is not None:
+            order.reset(0)
+        for j in range(C_):          # every context runs once, one after the other (graph capture, descriptor caches) ...
             fn(j, j)
+        if lane is not None:
+            lane.drain(C_)
         run_steps(fn, warmup)        # ... then `warmup` untimed steps through the scheduler
         torch.cuda.synchronize()
         if world > 1:
@@ -488,9 +523,13 @@ def main():
         e0.record(streams[0])
         for j in range(1, C_):
             streams[j].wait_event(e0)
-        last = run_steps(fn, steps)
+        last = run_steps(fn, steps)   # returns after the last gather of the run has completed
         for j in range(C_):
             ends[j].record(streams[j])
+        if gstream is not None:
+            eg = torch.cuda.Event(enable_timing=True)
+            eg.record(gstream)
+            ends.append(eg)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -539,12 +578,20 @@ def main():
     achieved = 2.0 * M_ * N_ * K_ / (gemm_ms * 1e-3) / 1e12
     torch.cuda.synchronize()
     phase_ms, enc_ms = None, None
-    order.reset(0)
-    step_resident(0, 0)                    # one isolated step: device times without cross-batch contention
+    def one_step():
+        if lane is not None:
+            lane.start(0)
+        if order is not None:
+            order.reset(0)
+        step_resident(0, 0)
+        if lane is not None:
+            lane.drain(1)
+
+    one_step()                             # one isolated step: device times without cross-batch contention
     if not is_mgp:
         phase_ms = ctx.omni_last_timing()
     ctx.set_option('profile_gemm', 1)
-    step_resident(0, 1)
+    one_step()
     g_ms, g_flops, g_n = ctx.profile_read()
     ctx.set_option('profile_gemm', 0)
     torch.cuda.synchronize()
@@ -575,7 +622,7 @@ def main():
         'data': 'synthetic', 'config': cfg,
         'run': {'in_flight_contexts_per_gpu': C_, 'weights_shared_by_contexts': True,
                 'weights_startup_s': weights_s, 'weights_path': 'alm_broadcast_weights (one NCCL broadcast of the converted '
-                'planes)' if world > 1 else 'alm_load_weights', 'gather': 'alm_gather_sequences inside every timed step'
+                'planes)' if world > 1 else 'alm_load_weights', 'gather': f'alm_gather_sequences for every timed step ({args.collectives}), all complete inside the timed region'
                 if world > 1 else 'n/a (1 GPU)', **({'options': args.opt} if args.opt else {})},
         'decoded_chars_per_sec': world * n_chars / (ms_per_step * 1e-3),
         'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},

@@ -105,3 +105,34 @@ def test_collective_order_runs_tickets_in_order_and_releases_waiters_on_failure(
         order.run(0, lambda: (_ for _ in ()).throw(ValueError('boom')))
     w.join(10)
     assert not w.is_alive() and len(errs) == 1
+
+
+def test_collective_lane_runs_in_ticket_order_without_blocking_the_submitters():
+    """dist.CollectiveLane: the compute threads submit their batch's gather and go on; ONE lane thread runs the gathers in
+    ticket order; drain() waits for them, a failing gather surfaces in drain() / submit() instead of hanging anyone."""
+    import threading
+    import time
+    import pytest
+    from advancedliteratemachinery_b200.dist import CollectiveLane
+    lane, seen = CollectiveLane(max_ahead=4, timeout_s=20.0), []
+    lane.start(0)
+
+    def worker(j):
+        for s in range(j, 12, 3):
+            time.sleep(0.01 * ((s * 7) % 3))
+            lane.submit(s, lambda s=s: (time.sleep(0.005), seen.append(s), s * s)[-1])
+    ts = [threading.Thread(target=worker, args=(j,)) for j in range(3)]
+    t0 = time.time()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    lane.drain(12)
+    assert seen == list(range(12)) and lane.result(11) == 121 and time.time() - t0 < 10
+    lane.start(0)
+    lane.submit(0, lambda: (_ for _ in ()).throw(ValueError('boom')))
+    with pytest.raises(RuntimeError):
+        lane.drain(1)
+    with pytest.raises(RuntimeError):
+        lane.submit(1, lambda: None)
+    lane.stop()
