@@ -14,10 +14,10 @@ Workloads (BASELINE.json `configs`; the default is the one the headline metric i
             (32 over 4 GPUs), throughput only, NO parity oracle
 
 A step = one batch through the whole path.  `value`: inputs resident in HBM; `e2e`: the same metric through the adapter
-with pinned HOST inputs, H2D and D2H inside the timed region.  With N > 1 GPUs every step has ONE all-gather of the
-decoded sequences (alm_gather_sequences, the library's own NCCL communicator on a dedicated context; one host thread per
-rank issues the gathers in batch order -- dist.CollectiveLane -- and the timed region ends when the last one has completed),
-and the weights reach the ranks by ONE NCCL broadcast of the converted planes (alm_broadcast_weights).
+with pinned HOST inputs, H2D and D2H inside the timed region.  With N > 1 GPUs every step ends with ONE all-gather of the
+decoded sequences (alm_gather_sequences, the library's own NCCL communicator; the contexts' host threads take turns in
+batch order, dist.CollectiveOrder) inside the timed region, and the weights reach the ranks by ONE NCCL broadcast of the
+converted planes (alm_broadcast_weights).
 
 `--impl reference` times the reference algorithm (the CPU oracle port: fp32, no KV cache, memory repeated per instance,
 transformer.py:74-100) on the host cores on the SAME workload: one page (omni / table / platypus) or 32 crops (mgpstr)
@@ -319,10 +319,10 @@ def main():
                     'their launch gaps.  0 = the workload default')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE', help='extra alm_set_option (A/B runs)')
     ap.add_argument('--ref-budget-s', type=float, default=330.0, help='reference arm: stop adding timed steps past this')
-    ap.add_argument('--collectives', default='lane', choices=['lane', 'order'], help='N > 1: who issues the per-batch gathers. '
-                    'lane = one host thread per rank on a dedicated context / communicator, the compute threads do not wait '
-                    '(dist.CollectiveLane); order = every compute thread gathers on its own context\'s communicator, taking '
-                    'turns in batch order (dist.CollectiveOrder; the A/B reference)')
+    ap.add_argument('--collectives', default='order', choices=['order', 'lane'], help='N > 1: who issues the per-batch gathers. '
+                    'order = every compute thread gathers on its own context\'s communicator, taking turns in batch order '
+                    '(dist.CollectiveOrder) [default]; lane = one host thread per rank on a dedicated context / communicator, '
+                    'the compute threads do not wait (dist.CollectiveLane; measured: no gain at 2 GPUs, lower e2e)')
     ap.add_argument('--watchdog-s', type=float, default=600.0, help='a timed phase that takes longer dumps every host '
                     'thread\'s stack to stderr and exits non-zero (a hung collective must not burn the GPU box)')
     ap.add_argument('--cpu-child', nargs=3, default=None, help=argparse.SUPPRESS)
