@@ -30,6 +30,20 @@ def test_bench_workloads_and_reference_config_agree():
     assert b.WORKLOADS['omni']['pt_len'] == 2 * b.N_INST == 128 and b.WORKLOADS['table']['pt_len'] == 512
 
 
+def test_roofline_traffic_comes_from_the_committed_captures_of_the_same_launch():
+    """`roofline.traffic` of the bench line is read from the ncu capture of the launch the line names (profiles/): the
+    file every workload points at exists, parses, and its DRAM bytes are of the order of the launch's algorithmic bytes."""
+    b = _bench()
+    for name, w in b.WORKLOADS.items():
+        f = w.get('gemm_ncu')
+        if not f:
+            continue
+        t = b.ncu_traffic_bytes(f)
+        assert t is not None and t > 0, (name, f)
+        M, N, K = w['gemm']
+        assert 0.3 < t / (M * K * 4 + N * K * 4 + M * N * 4) < 3.0, (name, t)
+
+
 def test_mgp_decoded_chars_counts_tokens_before_eos():
     import torch
     b = _bench()
