@@ -11,8 +11,11 @@
 //     item, 128-byte swizzle, rows 49..63 of every tile stay zero), so the loads of the next two windows are in flight
 //     while eight consumer warps (head = warp / 4, 16-query band = warp % 4) run the current one; no CTA-wide barrier in
 //     the loop;
-//   * the probabilities are normalised with one reciprocal per row and converted with packed cvt.rn.bf16x2 (the XU pipe --
-//     exponentials, divisions, scalar conversions -- was the busiest unit of the per-head kernel at 42 %).
+//   * the softmax runs in base 2 (scores carried as x log2 e, the staged bias pre-multiplied: one FFMA + MUFU.EX2 per
+//     probability), the probabilities are normalised with one reciprocal per row and converted with packed cvt.rn.bf16x2
+//     (the XU pipe -- accurate expf, per-element divisions, scalar conversions -- was the busiest unit of the per-head
+//     kernel at 42 %).
+// Measured (ncu, Swin stage-2 launch of a 16-page batch): 229 us against 310 us, DRAM read 482 MB = algorithmic.
 #include <algorithm>
 
 #include "alm_internal.h"
