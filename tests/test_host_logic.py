@@ -150,3 +150,44 @@ def test_collective_lane_runs_in_ticket_order_without_blocking_the_submitters():
     with pytest.raises(RuntimeError):
         lane.submit(1, lambda: None)
     lane.stop()
+
+
+def test_epilogue_and_window_staging_layouts_are_bijective_and_conflict_free():
+    """Integer restatement of the shared-memory addressing of the round-2 kernels (no GPU):
+    * TMA-store GEMM epilogue (csrc/gemm.cu, PLAIN == 2): lane r writes 16-byte chunk k of its 64-byte row at
+      r*64 + ((k ^ ((r >> 1) & 3)) << 4) -- the CU_TENSOR_MAP_SWIZZLE_64B pattern (address bits [4,5] ^= bits [7,8]); every
+      quarter-warp store covers 32 distinct banks and the block is filled exactly once;
+    * window_attention_ms (csrc/wattn_ms.cu): sw128(row, chunk) = row*128 + ((chunk ^ (row & 7)) << 4), the 128-byte swizzle
+      (bits [4,6] ^= bits [7,9]): the 8 rows of an ldmatrix 8x8 tile hit 8 distinct 16-byte bank groups; the bias pitch of 56
+      floats makes the float2 reads of a half-warp (4 rows x 4 column pairs) conflict-free."""
+    # --- 64-byte swizzle of the epilogue staging block (32 rows x 64 bytes)
+    seen = set()
+    for k in range(4):
+        for q in range(4):                                    # a 16-byte store is issued per quarter-warp (8 lanes)
+            banks = set()
+            for r in range(8 * q, 8 * q + 8):
+                a = r * 64 + ((k ^ ((r >> 1) & 3)) << 4)
+                assert a ^ (((a >> 7) & 3) << 4) == r * 64 + k * 16      # == hardware pattern applied to the linear address
+                seen.add(a)
+                banks.update(range((a // 4) % 32, (a // 4) % 32 + 4))
+            assert len(banks) == 32
+    assert seen == set(range(0, 2048, 16))
+    # --- 128-byte swizzle of the window tiles (64 rows x 128 bytes), ldmatrix row groups
+    sw128 = lambda row, chunk: row * 128 + ((chunk ^ (row & 7)) << 4)
+    for chunk in range(8):
+        for r0 in range(0, 64, 8):
+            groups = {(sw128(r0 + i, chunk) // 16) % 8 for i in range(8)}
+            assert len(groups) == 8
+            for i in range(8):
+                a = sw128(r0 + i, chunk)
+                assert a ^ (((a >> 7) & 7) << 4) == (r0 + i) * 128 + chunk * 16
+    # --- bias pitch: lanes (g, t) of a half-warp read float2 at row g (4 consecutive rows), columns 8j + 2t
+    pitch = 56
+    for j in range(7):
+        for half in range(2):
+            banks = []
+            for g in range(4 * half, 4 * half + 4):
+                for t in range(4):
+                    w0 = (16 + g) * pitch + 8 * j + 2 * t       # any band: the row offset only adds a multiple of the pitch
+                    banks += [w0 % 32, (w0 + 1) % 32]
+            assert len(set(banks)) == 32
